@@ -1,0 +1,179 @@
+/*
+ * nafae_b200.h -- C ABI of libnafae_b200.so: the B200-native (sm_100a) drop-in for the native
+ * layer of jshi31/NAFAE's per-segment grounding hot path.
+ *
+ * Conventions (shared by every entry point)
+ *   - plain C: raw DEVICE pointers, ints, floats and a cudaStream_t; no torch / THC types.
+ *   - return value: 1 = ok (the reference's convention, e.g. roi_align_cuda.c:41),
+ *                   0 = invalid argument (reference: `size_rois != 5` -> 0, roi_align_cuda.c:19-22),
+ *                  <0 = -(cudaError_t) of a failed launch.  Never exit()s (the reference's
+ *                   launchers call exit(-1), roi_align_kernel.cu:84-88), never prints.
+ *     nafae_last_error() returns a thread-local, human readable message for the last 0 / <0.
+ *   - stream ordered, asynchronous, no host synchronisation, no allocation: scratch memory is a
+ *     caller-provided workspace whose size the matching *_workspace_bytes() function returns.
+ *     Every entry point may be captured into a CUDA graph.
+ *   - all tensors are dense, row-major ("contiguous" in torch terms), fp32 unless stated.
+ *
+ * Each declaration cites the reference interface (path:line under the reference tree) it
+ * replaces.  INTEGRATION.md shows the binding a maintainer of the reference would add.
+ */
+#ifndef NAFAE_B200_H_
+#define NAFAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st* cudaStream_t; /* same opaque handle as CUDA driver_types.h */
+#endif
+
+#define NAFAE_B200_ABI_VERSION 1
+
+/* pooling applied on top of the sampled RoIAlign grid (modules/roi_align.py:6-42) */
+#define NAFAE_POOL_NONE 0 /* RoIAlign    : output is the aligned_height x aligned_width grid   */
+#define NAFAE_POOL_AVG 1  /* RoIAlignAvg : sample (h+1)x(w+1), avg_pool2d(kernel 2, stride 1)  */
+#define NAFAE_POOL_MAX 2  /* RoIAlignMax : sample (h+1)x(w+1), max_pool2d(kernel 2, stride 1)  */
+
+/* flags */
+#define NAFAE_FLAG_EXACT 1u /* reference-order arithmetic (mixed fp32/fp64 exactly as the
+                               reference kernel evaluates it): bit-identical pooled features,
+                               slower.  Default (0) = fp32 FMA path, <= 1e-4 relative. */
+
+int nafae_abi_version(void);
+const char* nafae_last_error(void);
+
+/* ------------------------------------------------------------------------------- NMS ---- */
+
+/* Replaces nms_cuda_compute() -- lib/model/nms/src/nms_cuda_kernel.h:5-6 (impl
+ * nms_cuda_kernel.cu:87-161) and its THC glue nms_cuda() -- lib/model/nms/src/nms_cuda.h:4-5.
+ * Same symbol, same argument meaning: boxes (boxes_num, boxes_dim>=4) rows [x1,y1,x2,y2,...]
+ * sorted by score descending, DEVICE memory (the reference's "boxes_host" is a device pointer
+ * too, nms_cuda.c:12-14); keep_out (boxes_num) int32 and num_out (1) int32 DEVICE buffers owned
+ * by the caller.  Greedy, IoU with the +1 pixel convention, strict '>' (nms_cuda_kernel.cu:31-39,
+ * 78).  Differences: no cudaMalloc/cudaFree, no D2H mask copy, no host sweep -- runs on the
+ * legacy default stream (like the reference's <<<blocks, threads>>>) using an internal
+ * per-device scratch cache, and returns without synchronising. */
+void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, int boxes_num, int boxes_dim,
+                      float nms_overlap_thresh);
+
+/* Batched, stream-ordered form of the same operator: F independent frames in one call.
+ * boxes (F, n, boxes_dim); keep_out (F, n) int32; num_out (F) int32.
+ * workspace: nafae_nms_workspace_bytes(F, n) bytes of device memory. */
+size_t nafae_nms_workspace_bytes(int num_frames, int boxes_num);
+int nafae_nms_batched(int* keep_out, int* num_out, const float* boxes, int num_frames,
+                      int boxes_num, int boxes_dim, float nms_overlap_thresh, void* workspace,
+                      size_t workspace_bytes, cudaStream_t stream);
+
+/* Replaces the per-frame Python loop of _ProposalLayer.forward --
+ * lib/model/rpn/proposal_layer.py:127-163 (slice to pre_nms_topN :139-140, nms() :150, first
+ * post_nms_topN keeps :154-155, zero padding + frame index in column 0 :158-163) -- for all
+ * frames in ONE launch, stopping each frame's greedy scan as soon as post_nms_topn boxes are
+ * kept.  proposals (F, n, 4) and scores (F, n) must already be in score-descending order per
+ * frame (the torch.sort of :125).  Outputs are fully written (padding included):
+ *   rois (F, post_nms_topn, 5) = [frame, x1, y1, x2, y2], roi_scores (F, post_nms_topn),
+ *   num_kept (F) int32 or NULL.  post_nms_topn <= 0 is invalid here (use nafae_nms_batched). */
+int nafae_proposal_tail(const float* proposals, const float* scores, int num_frames, int boxes_num,
+                        int pre_nms_topn, int post_nms_topn, float nms_thresh, float* rois,
+                        float* roi_scores, int* num_kept, cudaStream_t stream);
+
+/* -------------------------------------------------------------------------- RoIAlign ---- */
+
+/* Replace ROIAlignForwardLaucher / ROIAlignBackwardLaucher --
+ * lib/model/roi_align/src/roi_align_kernel.h:13-27 (impl roi_align_kernel.cu:73-91, 145-162);
+ * same symbols, same signatures.  bottom_data (B, C, H, W) NCHW; bottom_rois (R, 5) =
+ * [batch_index, x1, y1, x2, y2] in image coordinates; top_data (R, C, ah, aw).  Backward
+ * ACCUMULATES into bottom_diff, which the caller zero-fills (functions/roi_align.py:38-39).
+ * These two always use the reference-order arithmetic (NAFAE_FLAG_EXACT). */
+int ROIAlignForwardLaucher(const float* bottom_data, const float spatial_scale, const int num_rois,
+                           const int height, const int width, const int channels,
+                           const int aligned_height, const int aligned_width,
+                           const float* bottom_rois, float* top_data, cudaStream_t stream);
+int ROIAlignBackwardLaucher(const float* top_diff, const float spatial_scale, const int batch_size,
+                            const int num_rois, const int height, const int width,
+                            const int channels, const int aligned_height, const int aligned_width,
+                            const float* bottom_rois, float* bottom_diff, cudaStream_t stream);
+
+/* Fused module-level operator: RoIAlign / RoIAlignAvg / RoIAlignMax.forward --
+ * lib/model/roi_align/modules/roi_align.py:14-16, 26-29, 39-42 -- i.e. roi_align_forward_cuda
+ * (src/roi_align_cuda.h:1-2) plus the following avg_pool2d / max_pool2d, without the
+ * (R, C, h+1, w+1) intermediate.  out_height x out_width is the MODULE's aligned size (7x7 for
+ * RoIAlignAvg(7, 7, 1/16)); with pool_mode != NONE the sampled grid is (out+1) x (out+1).
+ * top_data (R, C, out_height, out_width) is fully written (no zero-fill needed).
+ * workspace: nafae_roi_align_workspace_bytes(batch_size, num_rois) bytes (may be 0 -> NULL ok). */
+size_t nafae_roi_align_workspace_bytes(int batch_size, int num_rois);
+int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size,
+                            int num_rois, int height, int width, int channels, int out_height,
+                            int out_width, int pool_mode, const float* bottom_rois, float* top_data,
+                            unsigned flags, void* workspace, size_t workspace_bytes,
+                            cudaStream_t stream);
+
+/* Backward of the fused operator (roi_align_backward_cuda, src/roi_align_cuda.h:4-5, preceded by
+ * the pool's backward that autograd derives).  top_diff (R, C, out_height, out_width);
+ * bottom_data is only read for NAFAE_POOL_MAX (may be NULL otherwise).  ACCUMULATES into
+ * bottom_diff (B, C, H, W), which the caller zero-fills. */
+int nafae_roi_align_backward(const float* top_diff, const float* bottom_data, float spatial_scale,
+                             int batch_size, int num_rois, int height, int width, int channels,
+                             int out_height, int out_width, int pool_mode, const float* bottom_rois,
+                             float* bottom_diff, unsigned flags, cudaStream_t stream);
+
+/* --------------------------------------------------------------------------- RoIPool ---- */
+
+/* Replace ROIPoolForwardLaucher / ROIPoolBackwardLaucher --
+ * lib/model/roi_pooling/src/roi_pooling_kernel.h:8-18 (impl roi_pooling_kernel.cu:95-125,
+ * 205-234); same symbols, same signatures.  argmax_data (R, C, ph, pw) int32 holds the flat index
+ * into the whole (B, C, H, W) batch, -1 for an empty bin; may be NULL in forward.  Backward
+ * OVERWRITES bottom_diff (gather form, roi_pooling_kernel.cu:147-201). */
+int ROIPoolForwardLaucher(const float* bottom_data, const float spatial_scale, const int num_rois,
+                          const int height, const int width, const int channels,
+                          const int pooled_height, const int pooled_width,
+                          const float* bottom_rois, float* top_data, int* argmax_data,
+                          cudaStream_t stream);
+int ROIPoolBackwardLaucher(const float* top_diff, const float spatial_scale, const int batch_size,
+                           const int num_rois, const int height, const int width,
+                           const int channels, const int pooled_height, const int pooled_width,
+                           const float* bottom_rois, float* bottom_diff, const int* argmax_data,
+                           cudaStream_t stream);
+
+/* ------------------------------------------------------- similarity + losses (DVSA) ---- */
+
+/* Replaces DVSA.forward -- model.py:517-614 -- and the backward autograd derives from it
+ * (model.py:772), as one fused forward kernel and one fused backward kernel.
+ *   vis_feats  (Na*Ns*Nb, D)   region embeddings, rows ordered (segment, frame, box)
+ *   word_feats (Na*Ne, D)      query embeddings, rows ordered (segment, padded entity slot)
+ *   entities_length (Na) int32 DEVICE: number of real queries per segment (0..Ne)
+ *   D_ind (Na*Ns, Na*Ne) int64, D_sim (Na*Ns, Na*Ne) f32: argmax / max over the Nb boxes of the
+ *     masked similarity (model.py:608-612; first maximal index on ties)
+ *   margin_loss (1) f32: 10*(mean(frame_score) + vis_lam*vis_loss) when train != 0, else
+ *     10*mean(frame_score)  (model.py:606)
+ * The workspace carries the saved state from forward to backward and must not be touched in
+ * between; it must be ZERO-FILLED ONCE after allocation (the kernels leave their arrival
+ * counters zeroed on exit).  grad_margin_loss (1) f32 DEVICE = dL/d(margin_loss).
+ * grad_vis (Na*Ns*Nb, D) and grad_word (Na*Ne, D) are fully written. */
+size_t nafae_ground_workspace_bytes(int Na, int Ns, int Nb, int Ne, int D);
+int nafae_ground_forward(const float* vis_feats, const float* word_feats,
+                         const int* entities_length, int Na, int Ns, int Nb, int Ne, int D,
+                         float Delta, float vis_lam, int train, int64_t* D_ind, float* D_sim,
+                         float* margin_loss, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream);
+int nafae_ground_backward(const float* grad_margin_loss, const float* vis_feats,
+                          const float* word_feats, const int* entities_length, int Na, int Ns,
+                          int Nb, int Ne, int D, float Delta, float vis_lam, int train,
+                          const int64_t* D_ind, const float* D_sim, float* grad_vis,
+                          float* grad_word, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream);
+
+/* Device-side postprocess -- model.py:457-474: keeps the a'==a diagonal blocks of D_ind / D_sim
+ * and turns the box index into a global row a*Ns*Nb + s*Nb + b.
+ * out_ind (Na, Ns, Ne) int64, out_sim (Na, Ns, Ne) f32. */
+int nafae_ground_postprocess(const int64_t* D_ind, const float* D_sim, int Na, int Ns, int Nb,
+                             int Ne, int64_t* out_ind, float* out_sim, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* NAFAE_B200_H_ */

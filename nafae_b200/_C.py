@@ -1,0 +1,110 @@
+"""ctypes binding of libnafae_b200.so (the C ABI declared in include/nafae_b200.h).
+
+This is the only place the shared library is loaded.  It fails loudly when the library is
+missing -- there is deliberately no CPU or PyTorch fallback.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnafae_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "nafae_b200: %s not found. Build it with `python -c 'import __graft_entry__ as g; "
+        "g.build()'` or `make -C nafae_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+c_int, c_float, c_size_t, c_void_p, c_uint = (ctypes.c_int, ctypes.c_float, ctypes.c_size_t,
+                                              ctypes.c_void_p, ctypes.c_uint)
+
+# name -> (restype, argtypes); kept in the order of include/nafae_b200.h
+SIGNATURES = {
+    "nafae_abi_version": (c_int, []),
+    "nafae_last_error": (ctypes.c_char_p, []),
+    "nms_cuda_compute": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float]),
+    "nafae_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "nafae_nms_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                  c_void_p, c_size_t, c_void_p]),
+    "nafae_proposal_tail": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ROIAlignForwardLaucher": (c_int, [c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p, c_void_p, c_void_p]),
+    "ROIAlignBackwardLaucher": (c_int, [c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "nafae_roi_align_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "nafae_roi_align_forward": (c_int, [c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, c_void_p, c_void_p, c_uint, c_void_p,
+                                        c_size_t, c_void_p]),
+    "nafae_roi_align_backward": (c_int, [c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_uint,
+                                         c_void_p]),
+    "ROIPoolForwardLaucher": (c_int, [c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ROIPoolBackwardLaucher": (c_int, [c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nafae_ground_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "nafae_ground_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_size_t, c_void_p]),
+    "nafae_ground_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                      c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nafae_ground_postprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                         c_void_p, c_void_p]),
+}
+
+MISSING = []
+for _name, (_res, _args) in SIGNATURES.items():
+    try:
+        _fn = getattr(lib, _name)
+    except AttributeError:
+        MISSING.append(_name)
+        continue
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
+FLAG_EXACT = 1
+
+
+class NafaeError(RuntimeError):
+    pass
+
+
+def last_error():
+    msg = lib.nafae_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status, what):
+    """1 = ok; 0 = invalid argument; <0 = -cudaError (include/nafae_b200.h)."""
+    if status != 1:
+        raise NafaeError("%s failed (status %d): %s" % (what, status, last_error()))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream(device=None):
+    """cudaStream_t of torch's current stream on `device`."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise NotImplementedError("%s must be a CUDA tensor: nafae_b200 has no CPU path" % name)
+
+
+def f32c(t, name):
+    require_cuda(t, name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()

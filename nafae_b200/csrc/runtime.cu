@@ -1,0 +1,40 @@
+// Error reporting and small host-side utilities shared by the entry points.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace nafae {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int launch_status(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return 1;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return -(int)e;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace nafae
+
+NAFAE_API int nafae_abi_version(void) { return NAFAE_B200_ABI_VERSION; }
+NAFAE_API const char* nafae_last_error(void) { return nafae::g_err; }
