@@ -1,0 +1,606 @@
+// Corner-grid RoIAlign (+ fused 2x2/stride-1 avg or max post pool) for sm_100a.
+//
+// Replaces (reference tree paths):
+//   lib/model/roi_align/src/roi_align_kernel.cu:15-70    ROIAlignForward
+//   lib/model/roi_align/src/roi_align_kernel.cu:94-143   ROIAlignBackward
+//   lib/model/roi_align/src/roi_align_kernel.cu:73-91,145-162  launchers (same symbols exported)
+//   lib/model/roi_align/modules/roi_align.py:26-29,39-42 RoIAlignAvg / RoIAlignMax (= kernel +
+//                                                        avg_pool2d / max_pool2d(2, 1))
+//
+// Semantics that are kept (they differ from torchvision's roi_align): the sampled points form
+// a corner grid with bin = max(end-start+1, 0)/(aligned-1); a sample outside [0,H)x[0,W) is 0;
+// cells are hstart = min(floor(h), H-2), so for h in [H-1, H) the weight h-hstart is in [1,2):
+// linear EXTRAPOLATION, not clamping (roi_align_kernel.cu:48-49, 57-67).
+//
+// Two arithmetic modes share one geometry routine (bit-identical in/out decisions and cells):
+//   exact : the reference's mixed fp32/fp64 expression exactly as nvcc compiles it (checked in
+//           SASS: which partial products are float, which DFMAs are fused) -> bit-identical output
+//   fast  : fp32 FMAs on the same taps -> |err| ~ 1e-7 relative, used by the bandwidth kernel
+//
+// Kernels:
+//   align_fwd_generic / align_bwd_generic   any shape, exact or fast; the *Laucher symbols
+//   align_pool_fwd_slab                     the hot path (7x7 out, 8x8 samples, avg or max):
+//       persistent CTAs, one (frame, channel-group) slab of the NCHW map at a time, staged into
+//       shared memory by 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier) in a
+//       3-stage ring; every feature byte is read from HBM exactly once, all RoIs of the frame
+//       are served from shared memory, the (R,C,8,8) intermediate never exists, and the 2x2
+//       pool is a register/shuffle epilogue.
+#include "common.cuh"
+
+namespace nafae {
+namespace {
+
+// ------------------------------------------------------------------------ geometry ----
+struct RoiGeom {
+  float start_w, start_h, bin_w, bin_h;
+  int batch;
+};
+
+// roi_align_kernel.cu:33-43 as compiled: end-start is fma(x2, s, -RN(x1*s)); "+ 1." in double
+// then fmaxf's float conversion is an exact float add; bin is a double division rounded to float.
+__device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ roi, float scale, int sh,
+                                            int sw) {
+  RoiGeom g;
+  g.batch = (int)roi[0];
+  g.start_w = __fmul_rn(roi[1], scale);
+  g.start_h = __fmul_rn(roi[2], scale);
+  const float rw = fmaxf(__fadd_rn(__fmaf_rn(roi[3], scale, -g.start_w), 1.f), 0.f);
+  const float rh = fmaxf(__fadd_rn(__fmaf_rn(roi[4], scale, -g.start_h), 1.f), 0.f);
+  g.bin_h = __double2float_rn(__ddiv_rn((double)rh, __dsub_rn((double)sh, 1.)));
+  g.bin_w = __double2float_rn(__ddiv_rn((double)rw, __dsub_rn((double)sw, 1.)));
+  return g;
+}
+
+// one axis of a sample point (roi_align_kernel.cu:45-49,54,58-59): returns false if outside
+__device__ __forceinline__ bool axis_sample(float start, float bin, int p, int extent, int* cell,
+                                            float* ratio) {
+  const float x = __fmaf_rn((float)p, bin, start);
+  if (x < 0.f || x >= (float)extent || x != x) {
+    *cell = 0;
+    *ratio = 0.f;
+    // NaN: the reference's comparisons are all false -> it would read out of bounds; we
+    // define the sample as outside instead.
+    return false;
+  }
+  const int c = (int)fminf(floorf(x), (float)(extent - 2));
+  *cell = c;
+  *ratio = __fsub_rn(x, (float)c);
+  return true;
+}
+
+// roi_align_kernel.cu:64-67 as compiled (see header comment)
+__device__ __forceinline__ float interp_exact(float ul, float ur, float dl, float dr, float hr,
+                                              float wr) {
+  const double omh = __dsub_rn(1., (double)hr);
+  const double omw = __dsub_rn(1., (double)wr);
+  const double t2 = __dmul_rn(__dmul_rn((double)ur, omh), (double)wr);
+  double s = __fma_rn(__dmul_rn((double)ul, omh), omw, t2);
+  s = __fma_rn(omw, (double)__fmul_rn(dl, hr), s);
+  s = __dadd_rn(s, (double)__fmul_rn(__fmul_rn(dr, hr), wr));
+  return __double2float_rn(s);
+}
+
+__device__ __forceinline__ float interp_fast(float ul, float ur, float dl, float dr, float hr,
+                                             float wr) {
+  const float omw = 1.f - wr;
+  const float top = fmaf(ur, wr, ul * omw);
+  const float bot = fmaf(dr, wr, dl * omw);
+  return fmaf(bot, hr, top * (1.f - hr));
+}
+
+template <bool EXACT>
+__device__ __forceinline__ float sample_point(const float* __restrict__ plane, int W,
+                                              const RoiGeom& g, int ph, int pw, int H) {
+  int hc, wc;
+  float hr, wr;
+  const bool okh = axis_sample(g.start_h, g.bin_h, ph, H, &hc, &hr);
+  const bool okw = axis_sample(g.start_w, g.bin_w, pw, W, &wc, &wr);
+  if (!(okh && okw)) return 0.f;
+  const float* p = plane + hc * W + wc;
+  const float ul = __ldg(p), ur = __ldg(p + 1), dl = __ldg(p + W), dr = __ldg(p + W + 1);
+  return EXACT ? interp_exact(ul, ur, dl, dr, hr, wr) : interp_fast(ul, ur, dl, dr, hr, wr);
+}
+
+// ATen's 2x2 window reductions, row-major order (avg: sum from 0 then /4; max: v > m || isnan)
+__device__ __forceinline__ float pool4(int mode, float a, float b, float c, float d) {
+  if (mode == NAFAE_POOL_AVG)
+    return __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d), 0.25f);
+  float m = -INFINITY;
+  if (a > m || a != a) m = a;
+  if (b > m || b != b) m = b;
+  if (c > m || c != c) m = c;
+  if (d > m || d != d) m = d;
+  return m;
+}
+// index (0..3) ATen's max_pool2d reports for the window: first maximum, NaN wins, default 0
+__device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
+  float m = -INFINITY;
+  int k = 0;
+  if (a > m || a != a) { m = a; k = 0; }
+  if (b > m || b != b) { m = b; k = 1; }
+  if (c > m || c != c) { m = c; k = 2; }
+  if (d > m || d != d) { m = d; k = 3; }
+  return k;
+}
+
+// ------------------------------------------------------------------ generic kernels ----
+// One thread per output element (n, c, oh, ow).  POOL none: one sample.  avg/max: the 2x2 window
+// of the (oh+1)x(ow+1) sample grid.  RoIs whose batch index is outside [0, B) produce zeros.
+template <bool EXACT>
+__global__ void __launch_bounds__(256)
+align_fwd_generic(const float* __restrict__ bottom, float scale, int B, long long total, int H,
+                  int W, int C, int oh_n, int ow_n, int pool, const float* __restrict__ rois,
+                  float* __restrict__ top) {
+  const int sh = pool ? oh_n + 1 : oh_n, sw = pool ? ow_n + 1 : ow_n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ow = (int)(idx % ow_n);
+    const int oh = (int)((idx / ow_n) % oh_n);
+    const int c = (int)((idx / ow_n / oh_n) % C);
+    const int n = (int)(idx / ow_n / oh_n / C);
+    const RoiGeom g = roi_geom(rois + (size_t)n * 5, scale, sh, sw);
+    float v = 0.f;
+    if (g.batch >= 0 && g.batch < B) {
+      const float* plane = bottom + ((size_t)g.batch * C + c) * H * W;
+      if (pool == NAFAE_POOL_NONE) {
+        v = sample_point<EXACT>(plane, W, g, oh, ow, H);
+      } else {
+        const float a = sample_point<EXACT>(plane, W, g, oh, ow, H);
+        const float b = sample_point<EXACT>(plane, W, g, oh, ow + 1, H);
+        const float cc = sample_point<EXACT>(plane, W, g, oh + 1, ow, H);
+        const float d = sample_point<EXACT>(plane, W, g, oh + 1, ow + 1, H);
+        v = pool4(pool, a, b, cc, d);
+      }
+    }
+    top[idx] = v;
+  }
+}
+
+// One thread per SAMPLE-grid element (n, c, ph, pw): gathers the gradient that reaches the sample
+// through the pool (avg: every containing window's g/4, ascending window order like ATen's
+// avg_pool2d backward; max: windows whose ATen argmax is this sample), then scatters it to the
+// four taps with the reference's weights (roi_align_kernel.cu:137-140 as compiled).
+template <bool EXACT>
+__global__ void __launch_bounds__(256)
+align_bwd_generic(const float* __restrict__ top_diff, const float* __restrict__ bottom,
+                  float scale, int B, long long total, int H, int W, int C, int oh_n, int ow_n,
+                  int pool, const float* __restrict__ rois, float* __restrict__ bottom_diff) {
+  const int sh = pool ? oh_n + 1 : oh_n, sw = pool ? ow_n + 1 : ow_n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int pw = (int)(idx % sw);
+    const int ph = (int)((idx / sw) % sh);
+    const int c = (int)((idx / sw / sh) % C);
+    const int n = (int)(idx / sw / sh / C);
+    const RoiGeom g = roi_geom(rois + (size_t)n * 5, scale, sh, sw);
+    if (g.batch < 0 || g.batch >= B) continue;
+    int hc, wc;
+    float hr, wr;
+    const bool okh = axis_sample(g.start_h, g.bin_h, ph, H, &hc, &hr);
+    const bool okw = axis_sample(g.start_w, g.bin_w, pw, W, &wc, &wr);
+    if (!(okh && okw)) continue;
+    const float* td = top_diff + ((size_t)n * C + c) * oh_n * ow_n;
+    float gs = 0.f;
+    if (pool == NAFAE_POOL_NONE) {
+      gs = td[ph * ow_n + pw];
+    } else {
+      const float* plane = bottom ? bottom + ((size_t)g.batch * C + c) * H * W : nullptr;
+      for (int i = max(ph - 1, 0); i <= min(ph, oh_n - 1); ++i)
+        for (int j = max(pw - 1, 0); j <= min(pw, ow_n - 1); ++j) {
+          const float gy = td[i * ow_n + j];
+          if (pool == NAFAE_POOL_AVG) {
+            gs = __fadd_rn(gs, __fmul_rn(gy, 0.25f));
+          } else {
+            const float a = sample_point<EXACT>(plane, W, g, i, j, H);
+            const float b = sample_point<EXACT>(plane, W, g, i, j + 1, H);
+            const float cc = sample_point<EXACT>(plane, W, g, i + 1, j, H);
+            const float d = sample_point<EXACT>(plane, W, g, i + 1, j + 1, H);
+            const int k = argmax4(a, b, cc, d);
+            if (i + (k >> 1) == ph && j + (k & 1) == pw) gs = __fadd_rn(gs, gy);
+          }
+        }
+    }
+    float* p = bottom_diff + ((size_t)g.batch * C + c) * H * W + hc * W + wc;
+    float g1, g2, g3, g4;
+    if (EXACT) {
+      const double a = __dmul_rn((double)gs, __dsub_rn(1., (double)hr));
+      const float omw = __fsub_rn(1.f, wr);  // "(1 - w_ratio)" is int - float
+      g1 = __double2float_rn(__dmul_rn(a, (double)omw));
+      g2 = __double2float_rn(__dmul_rn(a, (double)wr));
+      const float bq = __fmul_rn(gs, hr);
+      g3 = __fmul_rn(bq, omw);
+      g4 = __fmul_rn(bq, wr);
+    } else {
+      const float a = gs * (1.f - hr), bq = gs * hr, omw = 1.f - wr;
+      g1 = a * omw;
+      g2 = a * wr;
+      g3 = bq * omw;
+      g4 = bq * wr;
+    }
+    atomicAdd(p, g1);
+    atomicAdd(p + 1, g2);
+    atomicAdd(p + W, g3);
+    atomicAdd(p + W + 1, g4);
+  }
+}
+
+// --------------------------------------------------------------- bandwidth kernel ----
+// 7x7 output from an 8x8 sample grid (RoIAlignAvg/Max(7, 7, s): the only configuration the
+// reference instantiates, faster_rcnn/rpn.py:34).
+constexpr int kOut = 7;
+constexpr int kS = 8;             // sample grid side
+constexpr int kSlabThreads = 512;
+constexpr int kSlabWarps = kSlabThreads / 32;
+constexpr int kMaxRoiTable = 128;  // RoIs of one frame resident in the table at a time
+constexpr int kStagesMax = 4;
+
+struct RoiEntry {            // 128 B: everything a pass needs about one RoI
+  int hoff[kS];              // hstart * W, or -1 if that sample row is outside
+  float hr[kS];
+  int woff[kS];              // wstart, or -1 if that sample column is outside
+  float wr[kS];
+};
+
+struct SlabParams {
+  const float* bottom;
+  const float* rois;
+  float* top;
+  float scale;
+  int B, R, H, W, C;
+  int cg;          // channels per slab (multiple of 4)
+  int groups;      // C / cg
+  int hw;          // H*W
+  int hwp;         // padded per-channel stride in shared memory (floats), hwp % 32 == 8
+  int stages;
+  int units;       // B * groups
+};
+
+template <int POOL>
+__global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const SlabParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [stages][cg][hwp] floats | RoiEntry[kMaxRoiTable] | int roi_id[kMaxRoiTable] | bars
+  float* slabs = reinterpret_cast<float*>(smem_raw);
+  const size_t stage_floats = (size_t)p.cg * p.hwp;
+  RoiEntry* table = reinterpret_cast<RoiEntry*>(slabs + stage_floats * p.stages);
+  int* roi_id = reinterpret_cast<int*>(table + kMaxRoiTable);
+  uint64_t* full = reinterpret_cast<uint64_t*>(roi_id + kMaxRoiTable);
+  __shared__ int s_nroi, s_next, s_warp_cnt[kSlabWarps];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // contiguous unit range per CTA so that the RoI table is rebuilt at most ~twice
+  const int u_begin = (int)((long long)p.units * blockIdx.x / gridDim.x);
+  const int u_end = (int)((long long)p.units * (blockIdx.x + 1) / gridDim.x);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const uint32_t chan_bytes = (uint32_t)p.hw * 4u;
+  auto issue = [&](int u, int stage) {  // thread 0 only
+    const int f = u / p.groups, gidx = u % p.groups;
+    const float* src = p.bottom + ((size_t)f * p.C + (size_t)gidx * p.cg) * p.hw;
+    float* dst = slabs + stage_floats * stage;
+    mbar_arrive_expect_tx(&full[stage], chan_bytes * p.cg);
+    for (int c = 0; c < p.cg; ++c)
+      bulk_g2s(dst + (size_t)c * p.hwp, src + (size_t)c * p.hw, chan_bytes, &full[stage]);
+  };
+  if (tid == 0)
+    for (int s = 0; s < p.stages && u_begin + s < u_end; ++s) issue(u_begin + s, s);
+
+  // RoIs whose batch index is outside [0, B): defined as all-zero rows (CTA 0 writes them)
+  if (blockIdx.x == 0) {
+    for (int r = warp; r < p.R; r += kSlabWarps) {
+      const int b = (int)p.rois[(size_t)r * 5];
+      if (b < 0 || b >= p.B) {
+        float* o = p.top + (size_t)r * p.C * (kOut * kOut);
+        for (int i = lane; i < p.C * kOut * kOut; i += 32) o[i] = 0.f;
+      }
+    }
+  }
+
+  int cur_f = -1;
+  for (int u = u_begin; u < u_end; ++u) {
+    const int it = u - u_begin;
+    const int stage = it % p.stages;
+    const uint32_t parity = (uint32_t)(it / p.stages) & 1u;
+    const int f = u / p.groups, gidx = u % p.groups;
+    const float* slab = slabs + stage_floats * stage;
+    bool waited = false;
+
+    // the frame's RoIs are processed in table-sized chunks (ascending RoI index)
+    int r_next = 0;
+    bool first_chunk = true;
+    while (true) {
+      const bool reuse = first_chunk && cur_f == f && s_next >= p.R;  // table already holds f
+      if (!reuse) {
+        __syncthreads();  // previous users of the table are done
+        if (tid == 0) s_nroi = 0;
+        __syncthreads();
+        // ordered compaction of {r >= r_next : batch(r) == f}, at most kMaxRoiTable of them
+        int base_r = r_next;
+        while (base_r < p.R) {
+          const int r = base_r + tid;
+          const bool hit = r < p.R && (int)p.rois[(size_t)r * 5] == f;
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+          __syncthreads();
+          int before = s_nroi, tot = 0;
+          for (int w = 0; w < kSlabWarps; ++w) {
+            const int cw = s_warp_cnt[w];
+            if (w < warp) before += cw;
+            tot += cw;
+          }
+          const int pos = before + __popc(bal & ((1u << lane) - 1u));
+          if (hit && pos < kMaxRoiTable) roi_id[pos] = r;
+          __syncthreads();
+          const int filled = s_nroi + tot;
+          if (filled >= kMaxRoiTable) {
+            // find the first RoI index that did not fit: next chunk starts there
+            if (tid == 0) s_nroi = kMaxRoiTable;
+            int overflow_r = p.R;
+            if (hit && pos >= kMaxRoiTable) overflow_r = r;
+            // block-wide min via atomics on s_next
+            if (tid == 0) s_next = p.R;
+            __syncthreads();
+            if (overflow_r < p.R) atomicMin(&s_next, overflow_r);
+            __syncthreads();
+            if (s_next == p.R) {  // exactly filled: continue after this tile
+              if (tid == 0) s_next = min(base_r + kSlabThreads, p.R);
+              __syncthreads();
+            }
+            break;
+          }
+          if (tid == 0) s_nroi = filled;
+          base_r += kSlabThreads;
+          if (base_r >= p.R) {
+            if (tid == 0) s_next = p.R;
+          }
+          __syncthreads();
+        }
+        if (p.R == 0 && tid == 0) s_next = 0;
+        __syncthreads();
+        // geometry table: one thread per (RoI, axis, sample index)
+        const int nroi = s_nroi;
+        for (int e = tid; e < nroi * 2 * kS; e += kSlabThreads) {
+          const int j = e / (2 * kS), k = e % (2 * kS);
+          const RoiGeom g = roi_geom(p.rois + (size_t)roi_id[j] * 5, p.scale, kS, kS);
+          int cell;
+          float ratio;
+          if (k < kS) {
+            const bool ok = axis_sample(g.start_h, g.bin_h, k, p.H, &cell, &ratio);
+            table[j].hoff[k] = ok ? cell * p.W : -1;
+            table[j].hr[k] = ratio;
+          } else {
+            const bool ok = axis_sample(g.start_w, g.bin_w, k - kS, p.W, &cell, &ratio);
+            table[j].woff[k - kS] = ok ? cell : -1;
+            table[j].wr[k - kS] = ratio;
+          }
+        }
+        __syncthreads();
+        cur_f = f;
+      }
+      const int nroi = s_nroi;
+      const int next_after = s_next;
+      if (!waited) {
+        mbar_wait(&full[stage], parity);
+        waited = true;
+      }
+
+      // one pass = (RoI j, 4 consecutive channels); lane = (channel cq, sample column pw)
+      const int quads = p.cg >> 2;
+      const int cq = lane >> 3, pw = lane & 7;
+      for (int pass = warp; pass < nroi * quads; pass += kSlabWarps) {
+        const int j = pass / quads, q = pass % quads;
+        const RoiEntry& e = table[j];
+        const int wo = e.woff[pw];
+        const float wr = e.wr[pw];
+        const float* base = slab + (size_t)(q * 4 + cq) * p.hwp + (wo < 0 ? 0 : wo);
+        float s[kS];
+#pragma unroll
+        for (int ph = 0; ph < kS; ++ph) {
+          const int ho = e.hoff[ph];
+          const float* t = base + (ho < 0 ? 0 : ho);
+          const float v = interp_fast(t[0], t[1], t[p.W], t[p.W + 1], e.hr[ph], wr);
+          s[ph] = (ho < 0 || wo < 0) ? 0.f : v;
+        }
+        const int c = gidx * p.cg + q * 4 + cq;
+        float* o = p.top + ((size_t)roi_id[j] * p.C + c) * (kOut * kOut) + pw;
+        float right_prev = __shfl_down_sync(0xffffffffu, s[0], 1);
+#pragma unroll
+        for (int i = 0; i < kOut; ++i) {
+          const float right_next = __shfl_down_sync(0xffffffffu, s[i + 1], 1);
+          const float v = pool4(POOL, s[i], right_prev, s[i + 1], right_next);
+          if (pw < kOut) o[i * kOut] = v;
+          right_prev = right_next;
+        }
+      }
+      first_chunk = false;
+      if (next_after >= p.R) break;
+      r_next = next_after;
+    }
+
+    __syncthreads();  // every warp is done with this stage
+    if (tid == 0 && u + p.stages < u_end) issue(u + p.stages, stage);
+  }
+}
+
+int smem_optin_limit() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+      v = 48 * 1024;
+    cached = v;
+  }
+  return cached;
+}
+
+// Returns 1 if the slab kernel was launched, 0 if the shape is not eligible (caller falls back),
+// <0 on a launch error.
+int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W, int C, int pool,
+                    const float* rois, float* top, cudaStream_t stream) {
+  const int hw = H * W;
+  if (hw % 4 != 0 || C % 4 != 0 || H < 2 || W < 2) return 0;
+  if ((reinterpret_cast<uintptr_t>(bottom) & 15) != 0) return 0;
+  if ((long long)R * 5 >= (1ll << 31)) return 0;
+  int hwp = hw;
+  while (hwp % 32 != 8) hwp += 4;
+  const size_t fixed = sizeof(RoiEntry) * kMaxRoiTable + sizeof(int) * kMaxRoiTable +
+                       sizeof(uint64_t) * kStagesMax + 128;
+  const size_t budget = (size_t)smem_optin_limit() - 1024;  // static smem + slack
+  int cg = 0, stages = 0;
+  // prefer >= 3 stages with a slab of <= 64 KB
+  for (int cand : {32, 16, 8, 4}) {
+    if (C % cand) continue;
+    const size_t stage_bytes = (size_t)cand * hwp * 4;
+    if (stage_bytes > 64 * 1024 && cand > 4) continue;
+    int st = (int)((budget - fixed) / stage_bytes);
+    if (st > kStagesMax) st = kStagesMax;
+    if (st >= 2) {
+      cg = cand;
+      stages = st;
+      break;
+    }
+  }
+  if (cg == 0) return 0;
+  if ((size_t)hw * 4 * cg >= (1u << 20)) return 0;  // mbarrier tx-count range
+  SlabParams p;
+  p.bottom = bottom;
+  p.rois = rois;
+  p.top = top;
+  p.scale = scale;
+  p.B = B;
+  p.R = R;
+  p.H = H;
+  p.W = W;
+  p.C = C;
+  p.cg = cg;
+  p.groups = C / cg;
+  p.hw = hw;
+  p.hwp = hwp;
+  p.stages = stages;
+  p.units = B * p.groups;
+  const size_t smem = (size_t)cg * hwp * 4 * stages + fixed;
+  auto kern = pool == NAFAE_POOL_AVG ? align_pool_fwd_slab<NAFAE_POOL_AVG>
+                                     : align_pool_fwd_slab<NAFAE_POOL_MAX>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("roi_align: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    return -(int)e;
+  }
+  int grid = sm_count();
+  if (grid > p.units) grid = p.units;
+  kern<<<grid, kSlabThreads, smem, stream>>>(p);
+  return launch_status("align_pool_fwd_slab");
+}
+
+int grid_for(long long total) {
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+}  // namespace nafae
+
+using namespace nafae;
+
+NAFAE_API size_t nafae_roi_align_workspace_bytes(int batch_size, int num_rois) {
+  (void)batch_size;
+  (void)num_rois;
+  return 0;  // the RoI-per-frame lists live in shared memory; no device scratch needed
+}
+
+NAFAE_API int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size,
+                                      int num_rois, int height, int width, int channels,
+                                      int out_height, int out_width, int pool_mode,
+                                      const float* bottom_rois, float* top_data, unsigned flags,
+                                      void* workspace, size_t workspace_bytes,
+                                      cudaStream_t stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  NAFAE_REQUIRE(batch_size >= 0 && num_rois >= 0 && channels >= 0, "roi_align: negative sizes");
+  NAFAE_REQUIRE(pool_mode >= NAFAE_POOL_NONE && pool_mode <= NAFAE_POOL_MAX,
+                "roi_align: bad pool_mode %d", pool_mode);
+  NAFAE_REQUIRE(out_height >= 1 && out_width >= 1, "roi_align: bad output size %dx%d", out_height,
+                out_width);
+  const long long total = (long long)num_rois * channels * out_height * out_width;
+  if (total == 0) return 1;
+  NAFAE_REQUIRE(height >= 2 && width >= 2, "roi_align: feature map must be at least 2x2");
+  NAFAE_REQUIRE(bottom_data && bottom_rois && top_data, "roi_align: NULL buffer");
+  const bool exact = (flags & NAFAE_FLAG_EXACT) != 0;
+  if (!exact && pool_mode != NAFAE_POOL_NONE && out_height == kOut && out_width == kOut &&
+      batch_size > 0) {
+    const int st = try_launch_slab(bottom_data, spatial_scale, batch_size, num_rois, height, width,
+                                   channels, pool_mode, bottom_rois, top_data, stream);
+    if (st != 0) return st;
+  }
+  const int grid = grid_for(total);
+  if (exact)
+    align_fwd_generic<true><<<grid, 256, 0, stream>>>(bottom_data, spatial_scale, batch_size, total,
+                                                      height, width, channels, out_height,
+                                                      out_width, pool_mode, bottom_rois, top_data);
+  else
+    align_fwd_generic<false><<<grid, 256, 0, stream>>>(bottom_data, spatial_scale, batch_size,
+                                                       total, height, width, channels, out_height,
+                                                       out_width, pool_mode, bottom_rois, top_data);
+  return launch_status("align_fwd_generic");
+}
+
+NAFAE_API int nafae_roi_align_backward(const float* top_diff, const float* bottom_data,
+                                       float spatial_scale, int batch_size, int num_rois,
+                                       int height, int width, int channels, int out_height,
+                                       int out_width, int pool_mode, const float* bottom_rois,
+                                       float* bottom_diff, unsigned flags, cudaStream_t stream) {
+  NAFAE_REQUIRE(batch_size >= 0 && num_rois >= 0 && channels >= 0, "roi_align: negative sizes");
+  NAFAE_REQUIRE(pool_mode >= NAFAE_POOL_NONE && pool_mode <= NAFAE_POOL_MAX,
+                "roi_align: bad pool_mode %d", pool_mode);
+  NAFAE_REQUIRE(out_height >= 1 && out_width >= 1, "roi_align: bad output size");
+  NAFAE_REQUIRE(pool_mode != NAFAE_POOL_MAX || bottom_data,
+                "roi_align backward: max pooling needs bottom_data");
+  const int sh = pool_mode ? out_height + 1 : out_height, sw = pool_mode ? out_width + 1 : out_width;
+  const long long total = (long long)num_rois * channels * sh * sw;
+  if (total == 0 || batch_size == 0) return 1;
+  NAFAE_REQUIRE(height >= 2 && width >= 2, "roi_align: feature map must be at least 2x2");
+  NAFAE_REQUIRE(top_diff && bottom_rois && bottom_diff, "roi_align: NULL buffer");
+  const int grid = grid_for(total);
+  if (flags & NAFAE_FLAG_EXACT)
+    align_bwd_generic<true><<<grid, 256, 0, stream>>>(top_diff, bottom_data, spatial_scale,
+                                                      batch_size, total, height, width, channels,
+                                                      out_height, out_width, pool_mode,
+                                                      bottom_rois, bottom_diff);
+  else
+    align_bwd_generic<false><<<grid, 256, 0, stream>>>(top_diff, bottom_data, spatial_scale,
+                                                       batch_size, total, height, width, channels,
+                                                       out_height, out_width, pool_mode,
+                                                       bottom_rois, bottom_diff);
+  return launch_status("align_bwd_generic");
+}
+
+// Reference-named launchers (roi_align_kernel.h:13-27).  The reference never checks the batch
+// index; here it must lie in [0, 2^20) (rows outside the real batch are the caller's bug there too).
+NAFAE_API int ROIAlignForwardLaucher(const float* bottom_data, const float spatial_scale,
+                                     const int num_rois, const int height, const int width,
+                                     const int channels, const int aligned_height,
+                                     const int aligned_width, const float* bottom_rois,
+                                     float* top_data, cudaStream_t stream) {
+  return nafae_roi_align_forward(bottom_data, spatial_scale, 1 << 20, num_rois, height, width,
+                                 channels, aligned_height, aligned_width, NAFAE_POOL_NONE,
+                                 bottom_rois, top_data, NAFAE_FLAG_EXACT, nullptr, 0, stream);
+}
+
+NAFAE_API int ROIAlignBackwardLaucher(const float* top_diff, const float spatial_scale,
+                                      const int batch_size, const int num_rois, const int height,
+                                      const int width, const int channels,
+                                      const int aligned_height, const int aligned_width,
+                                      const float* bottom_rois, float* bottom_diff,
+                                      cudaStream_t stream) {
+  return nafae_roi_align_backward(top_diff, nullptr, spatial_scale, batch_size, num_rois, height,
+                                  width, channels, aligned_height, aligned_width, NAFAE_POOL_NONE,
+                                  bottom_rois, bottom_diff, NAFAE_FLAG_EXACT, stream);
+}
