@@ -234,7 +234,7 @@ constexpr int kSlabWarps = kSlabThreads / 32;
 constexpr int kMaxRoiTable = 128;  // RoIs of one frame resident in the table at a time
 constexpr int kStagesMax = 4;
 
-struct RoiEntry {            // 128 B: everything a pass needs about one RoI
+struct __align__(16) RoiEntry {  // 128 B: everything a pass needs about one RoI
   int hoff[kS];              // hstart * W, or -1 if that sample row is outside
   float hr[kS];
   int woff[kS];              // wstart, or -1 if that sample column is outside
@@ -300,7 +300,66 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
     }
   }
 
-  int cur_f = -1;
+  // Fill the RoI table with the next (at most kMaxRoiTable) RoIs of frame f whose index is
+  // >= r_start, in ascending index order; s_next = index where the following chunk starts
+  // (>= R when the frame is exhausted).
+  auto build_table = [&](int f, int r_start) {
+    __syncthreads();  // every warp is done with the previous table contents
+    if (tid == 0) {
+      s_nroi = 0;
+      s_next = p.R;
+    }
+    __syncthreads();
+    for (int base = r_start; base < p.R; base += kSlabThreads) {
+      const int r = base + tid;
+      const bool hit = r < p.R && (int)p.rois[(size_t)r * 5] == f;
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+      __syncthreads();
+      const int have = s_nroi;
+      int before = have, tot = 0;
+      for (int w = 0; w < kSlabWarps; ++w) {
+        const int cw = s_warp_cnt[w];
+        if (w < warp) before += cw;
+        tot += cw;
+      }
+      const int pos = before + __popc(bal & ((1u << lane) - 1u));
+      if (hit && pos < kMaxRoiTable) roi_id[pos] = r;
+      if (hit && pos == kMaxRoiTable) s_next = r;  // first RoI that did not fit (unique thread)
+      __syncthreads();
+      if (have + tot >= kMaxRoiTable) {  // uniform
+        if (tid == 0) {
+          s_nroi = kMaxRoiTable;
+          if (have + tot == kMaxRoiTable) s_next = min(base + kSlabThreads, p.R);
+        }
+        break;
+      }
+      if (tid == 0) s_nroi = have + tot;
+    }
+    __syncthreads();
+    const int nroi = s_nroi;
+    // geometry: one thread per (RoI, axis, sample index)
+    for (int e = tid; e < nroi * 2 * kS; e += kSlabThreads) {
+      const int j = e / (2 * kS), k = e % (2 * kS);
+      const RoiGeom g = roi_geom(p.rois + (size_t)roi_id[j] * 5, p.scale, kS, kS);
+      int cell;
+      float ratio;
+      if (k < kS) {
+        const bool ok = axis_sample(g.start_h, g.bin_h, k, p.H, &cell, &ratio);
+        table[j].hoff[k] = ok ? cell * p.W : -1;
+        table[j].hr[k] = ratio;
+      } else {
+        const bool ok = axis_sample(g.start_w, g.bin_w, k - kS, p.W, &cell, &ratio);
+        table[j].woff[k - kS] = ok ? cell : -1;
+        table[j].wr[k - kS] = ratio;
+      }
+    }
+    __syncthreads();
+  };
+
+  int cur_f = -1, cur_start = -1;  // which (frame, chunk start) the table holds
+  const int quads = p.cg >> 2;
+  const int cq = lane >> 3, pw = lane & 7;
   for (int u = u_begin; u < u_end; ++u) {
     const int it = u - u_begin;
     const int stage = it % p.stages;
@@ -308,78 +367,12 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
     const int f = u / p.groups, gidx = u % p.groups;
     const float* slab = slabs + stage_floats * stage;
     bool waited = false;
-
-    // the frame's RoIs are processed in table-sized chunks (ascending RoI index)
     int r_next = 0;
-    bool first_chunk = true;
-    while (true) {
-      const bool reuse = first_chunk && cur_f == f && s_next >= p.R;  // table already holds f
-      if (!reuse) {
-        __syncthreads();  // previous users of the table are done
-        if (tid == 0) s_nroi = 0;
-        __syncthreads();
-        // ordered compaction of {r >= r_next : batch(r) == f}, at most kMaxRoiTable of them
-        int base_r = r_next;
-        while (base_r < p.R) {
-          const int r = base_r + tid;
-          const bool hit = r < p.R && (int)p.rois[(size_t)r * 5] == f;
-          const unsigned bal = __ballot_sync(0xffffffffu, hit);
-          if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-          __syncthreads();
-          int before = s_nroi, tot = 0;
-          for (int w = 0; w < kSlabWarps; ++w) {
-            const int cw = s_warp_cnt[w];
-            if (w < warp) before += cw;
-            tot += cw;
-          }
-          const int pos = before + __popc(bal & ((1u << lane) - 1u));
-          if (hit && pos < kMaxRoiTable) roi_id[pos] = r;
-          __syncthreads();
-          const int filled = s_nroi + tot;
-          if (filled >= kMaxRoiTable) {
-            // find the first RoI index that did not fit: next chunk starts there
-            if (tid == 0) s_nroi = kMaxRoiTable;
-            int overflow_r = p.R;
-            if (hit && pos >= kMaxRoiTable) overflow_r = r;
-            // block-wide min via atomics on s_next
-            if (tid == 0) s_next = p.R;
-            __syncthreads();
-            if (overflow_r < p.R) atomicMin(&s_next, overflow_r);
-            __syncthreads();
-            if (s_next == p.R) {  // exactly filled: continue after this tile
-              if (tid == 0) s_next = min(base_r + kSlabThreads, p.R);
-              __syncthreads();
-            }
-            break;
-          }
-          if (tid == 0) s_nroi = filled;
-          base_r += kSlabThreads;
-          if (base_r >= p.R) {
-            if (tid == 0) s_next = p.R;
-          }
-          __syncthreads();
-        }
-        if (p.R == 0 && tid == 0) s_next = 0;
-        __syncthreads();
-        // geometry table: one thread per (RoI, axis, sample index)
-        const int nroi = s_nroi;
-        for (int e = tid; e < nroi * 2 * kS; e += kSlabThreads) {
-          const int j = e / (2 * kS), k = e % (2 * kS);
-          const RoiGeom g = roi_geom(p.rois + (size_t)roi_id[j] * 5, p.scale, kS, kS);
-          int cell;
-          float ratio;
-          if (k < kS) {
-            const bool ok = axis_sample(g.start_h, g.bin_h, k, p.H, &cell, &ratio);
-            table[j].hoff[k] = ok ? cell * p.W : -1;
-            table[j].hr[k] = ratio;
-          } else {
-            const bool ok = axis_sample(g.start_w, g.bin_w, k - kS, p.W, &cell, &ratio);
-            table[j].woff[k - kS] = ok ? cell : -1;
-            table[j].wr[k - kS] = ratio;
-          }
-        }
-        __syncthreads();
+    do {
+      if (!(cur_f == f && cur_start == r_next)) {
+        build_table(f, r_next);
         cur_f = f;
+        cur_start = r_next;
       }
       const int nroi = s_nroi;
       const int next_after = s_next;
@@ -387,10 +380,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
         mbar_wait(&full[stage], parity);
         waited = true;
       }
-
       // one pass = (RoI j, 4 consecutive channels); lane = (channel cq, sample column pw)
-      const int quads = p.cg >> 2;
-      const int cq = lane >> 3, pw = lane & 7;
       for (int pass = warp; pass < nroi * quads; pass += kSlabWarps) {
         const int j = pass / quads, q = pass % quads;
         const RoiEntry& e = table[j];
@@ -416,10 +406,8 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
           right_prev = right_next;
         }
       }
-      first_chunk = false;
-      if (next_after >= p.R) break;
       r_next = next_after;
-    }
+    } while (r_next < p.R);
 
     __syncthreads();  // every warp is done with this stage
     if (tid == 0 && u + p.stages < u_end) issue(u + p.stages, stage);
