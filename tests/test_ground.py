@@ -1,0 +1,140 @@
+"""Similarity / loss head parity: fused CUDA kernels vs the reference-generated fixtures and the
+torch CPU restatement (oracle/dvsa.py)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from _golden import check_grads_against_fixture, dvsa_case_names, dvsa_inputs, load_dvsa_case
+from nafae_b200 import synth
+from oracle import dvsa as odvsa
+
+gpu = pytest.mark.gpu
+# fp32 FMA path; north_star: <= 1e-4 relative for losses / similarities / gradients
+RTOL = 1e-4
+
+
+def _run(case, vis, word, lens=None):
+    from nafae_b200.grounding import ground
+    dev = torch.device("cuda:0")
+    v = torch.from_numpy(vis).to(dev).requires_grad_(True)
+    w = torch.from_numpy(word).to(dev).requires_grad_(True)
+    D_ind, D_sim, loss = ground(v, w, case["lens"] if lens is None else lens, case["Na"],
+                                case["Nb"], case["Ne"], case["Delta"], case["vis_lam"],
+                                case["phase"] == "train")
+    torch.nn.functional.l1_loss(loss, torch.zeros_like(loss)).backward()  # model.py:771-772
+    return (D_ind.cpu().numpy(), D_sim.cpu().numpy(), float(loss), v.grad.cpu().numpy(),
+            w.grad.cpu().numpy())
+
+
+def _live_mask(case):
+    m = np.zeros((case["Na"], case["Ne"]), bool)
+    for a, n in enumerate(case["lens"]):
+        m[a, :n] = True
+    return m.reshape(-1)
+
+
+@gpu
+@pytest.mark.parametrize("name", dvsa_case_names())
+def test_matches_reference_fixture(name):
+    case, z = load_dvsa_case(name)
+    vis, word = dvsa_inputs(case)
+    D_ind, D_sim, loss, gv, gw = _run(case, vis, word)
+    live = _live_mask(case)
+    # picks: bit-exact on every column (masked columns are all-zero ties -> index 0 in both)
+    np.testing.assert_array_equal(D_ind, z["D_ind"].astype(np.int64))
+    np.testing.assert_allclose(D_sim, z["D_sim"], rtol=RTOL, atol=1e-5)
+    assert not D_sim[:, ~live].any()
+    if np.isnan(z["margin_loss"]):
+        assert np.isnan(loss)
+        return
+    np.testing.assert_allclose(loss, z["margin_loss"], rtol=RTOL)
+    check_grads_against_fixture(z, gv, gw, rtol=RTOL, atol_scale=1e-5)
+
+
+@gpu
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_batches_match_oracle(seed):
+    """cfg2 shapes with histogram-sampled query counts (incl. empty segments)."""
+    c = synth.CONFIGS["cfg2"]
+    rs = np.random.RandomState(100 + seed)
+    lens = synth.entity_lengths(rs, c["Na"], c["Ne"])
+    vis = synth.embeddings(rs, c["Na"] * c["Ns"] * c["Nb"], c["D"])
+    word = synth.embeddings(rs, c["Na"] * c["Ne"], c["D"])
+    case = dict(Na=c["Na"], Nb=c["Nb"], Ne=c["Ne"], Delta=c["Delta"], vis_lam=c["vis_lam"],
+                phase="train", lens=lens)
+    D_ind, D_sim, loss, gv, gw = _run(case, vis, word)
+    ref = odvsa.dvsa_forward_backward(vis, word, lens, c["Na"], c["Nb"], c["Ne"], c["Delta"],
+                                      c["vis_lam"], "train")
+    live = _live_mask(case)
+    np.testing.assert_array_equal(D_ind[:, live], ref["D_ind"][:, live])
+    np.testing.assert_allclose(D_sim, ref["D_sim"], rtol=RTOL, atol=1e-5)
+    np.testing.assert_allclose(loss, ref["margin_loss"], rtol=RTOL)
+    for got, want in ((gv, ref["grad_vis"]), (gw, ref["grad_word"])):
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-5 * np.abs(want).max())
+
+
+@gpu
+def test_small_delta_activates_and_deactivates_hinges():
+    rs = np.random.RandomState(7)
+    Na, Ns, Nb, Ne, D = 4, 3, 6, 5, 64
+    lens = [2, 5, 1, 3]
+    vis = synth.embeddings(rs, Na * Ns * Nb, D)
+    word = synth.embeddings(rs, Na * Ne, D)
+    for Delta in (0.0, 0.3, 2.0):
+        case = dict(Na=Na, Nb=Nb, Ne=Ne, Delta=Delta, vis_lam=0.7, phase="train", lens=lens)
+        D_ind, D_sim, loss, gv, gw = _run(case, vis, word)
+        ref = odvsa.dvsa_forward_backward(vis, word, lens, Na, Nb, Ne, Delta, 0.7, "train")
+        np.testing.assert_allclose(loss, ref["margin_loss"], rtol=RTOL)
+        for got, want in ((gv, ref["grad_vis"]), (gw, ref["grad_word"])):
+            np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-5 * np.abs(want).max())
+
+
+@gpu
+def test_module_surface_and_postprocess():
+    from nafae_b200.grounding import DVSA, postprocess, record_det
+    case, z = load_dvsa_case("small_train")
+    vis, word = dvsa_inputs(case)
+    args = types.SimpleNamespace(batch_size=case["Na"], batch_size_val=1, max_ent_len=case["Ne"],
+                                 Delta=case["Delta"], vis_lam=case["vis_lam"])
+    cfg = types.SimpleNamespace(TEST=types.SimpleNamespace(RPN_POST_NMS_TOP_N=case["Nb"]))
+    dvsa = DVSA(args, cfg).cuda()
+    with pytest.raises(RuntimeError):
+        dvsa(torch.from_numpy(vis).cuda(), torch.from_numpy(word).cuda(), case["lens"])
+    dvsa.init_train()
+    D_ind, D_sim, loss = dvsa(torch.from_numpy(vis).cuda(), torch.from_numpy(word).cuda(),
+                              case["lens"])
+    assert D_ind.dtype == torch.int64 and D_ind.shape == (case["Na"] * case["Ns"],
+                                                          case["Na"] * case["Ne"])
+    assert loss.dim() == 0
+    np.testing.assert_allclose(float(loss), z["margin_loss"], rtol=RTOL)
+    # device postprocess and the numpy calling convention of the reference (model.py:457-474)
+    Dp, Sp = postprocess(D_ind, D_sim, case["Na"], case["Ns"], case["Nb"], case["Ne"])
+    np.testing.assert_array_equal(Dp.cpu().numpy(), z["post_D"])
+    Dn, Sn = postprocess(D_ind.cpu().numpy(), D_sim.cpu().numpy(), case["Na"], case["Ns"],
+                         case["Nb"], case["Ne"])
+    np.testing.assert_array_equal(Dn, z["post_D"])
+    np.testing.assert_allclose(Sn, z["post_D_sim"], rtol=RTOL, atol=1e-5)
+    # record_det bookkeeping equals the oracle's
+    ents = [["a", "b"], [], ["c", "d", "e", "f"]]
+    boxes = np.arange(case["Na"] * case["Ns"] * case["Nb"] * 4).reshape(-1, 4)
+    ids = ["img%d" % i for i in range(case["Na"] * case["Ns"])]
+    got = ([], [], [], [])
+    record_det(got[0], got[1], got[2], got[3], case["Nb"], ents, Dn, Sn, ids, boxes)
+    want = odvsa.record_det(case["Nb"], ents, z["post_D"], z["post_D_sim"], ids, boxes)
+    assert got[0] == want[0] and got[1] == want[1]
+    np.testing.assert_array_equal(np.asarray(got[2]), np.asarray(want[2]))
+
+
+@gpu
+def test_repeated_steps_reuse_workspace_cleanly():
+    """The kernels must leave counters / accumulators zeroed: step N+1 equals step 1."""
+    case, z = load_dvsa_case("cfg2_train")
+    vis, word = dvsa_inputs(case)
+    first = _run(case, vis, word)
+    for _ in range(3):
+        again = _run(case, vis, word)
+        np.testing.assert_array_equal(again[0], first[0])
+        assert again[2] == first[2]
+        np.testing.assert_allclose(again[3], first[3], rtol=1e-5, atol=1e-7)
