@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Headline benchmark: video segments/sec of the NAFAE grounding hot path (fwd+bwd) on B200.
+
+    python bench.py --gpus 1 --steps 200 --warmup 20
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 5 --warmup 1      # CPU arm (oracle port, host cores)
+
+One "step" = one batch of synthetic YouCookII-shaped segments (BASELINE.json configs[1], "cfg2":
+8 segments x 5 frames, 2352 proposals/frame -> NMS 0.7 -> top-20 -> RoIAlignAvg 7x7 over
+512x38x50 conv5 maps -> similarity + ranking/clustering losses forward and backward) through
+
+    proposal_tail -> align_pool_fwd_slab -> ground_fwd -> ground_bwd_cluster -> ground_bwd_main
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "video segments/sec (grounding head fwd+bwd)"
+UNIT = "segments/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg", default="cfg2", choices=["cfg2", "cfg2_real", "cfg4"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(cfg_name, world):
+    from nafae_b200 import synth
+    c = synth.CONFIGS[cfg_name]
+    return {
+        "workload": "%s: %d segments x %d frames/GPU/step, %d proposals/frame -> NMS 0.7 -> top-%d, "
+                    "RoIAlignAvg 7x7 on %dx%dx%d conv5 maps, %d query slots x %d-d, %s phase"
+                    % (cfg_name, c["Na"], c["Ns"], c["n"], c["Nb"], c["C"], c["H"], c["W"],
+                       c["Na"] * c["Ne"], c["D"], "train" if c["train"] else "eval"),
+        "segments_per_gpu_per_step": c["Na"],
+        "global_segments_per_step": c["Na"] * world,
+        "parallelism": "dp%d" % world,
+        "l2": "inputs larger than L2: two alternating input sets, %.0f MB of maps + %.0f MB of "
+              "pooled output per step vs 126 MB L2" % (
+                  c["Na"] * c["Ns"] * c["C"] * c["H"] * c["W"] * 4 / 1e6,
+                  c["Na"] * c["Ns"] * c["Nb"] * c["C"] * 49 * 4 / 1e6),
+    }
+
+
+# ------------------------------------------------------------------ CPU arm (oracle) ----
+def cpu_step(batch, c):
+    """The reference path on host cores: restated NMS tail + RoIAlignAvg (C, OpenMP) and the
+    torch-CPU restatement of DVSA forward + backward (oracle/; SURVEY.md section 8d "ref-cpu")."""
+    from oracle import cpu as ocpu
+    from oracle import dvsa as odvsa
+    rois, rsc, _ = ocpu.proposal_tail(batch["proposals"], batch["scores"], c["pre"], c["Nb"], 0.7)
+    pooled = ocpu.roi_align_avg_forward(batch["features"], rois.reshape(-1, 5), 7, 7, 1.0 / 16.0)
+    out = odvsa.dvsa_forward_backward(batch["vis_feats"], batch["word_feats"], batch["lens"],
+                                      c["Na"], c["Nb"], c["Ne"], c["Delta"], c["vis_lam"],
+                                      "train" if c["train"] else "eval")
+    return pooled, out
+
+
+def time_cpu(cfg_name, steps, warmup):
+    import torch
+    from nafae_b200 import synth
+    from oracle import cpu as ocpu
+    c = synth.CONFIGS[cfg_name]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ocpu.set_num_threads(cores)
+    batches = [synth.make_batch(cfg_name, 1234 + i) for i in range(2)]
+    for i in range(warmup):
+        cpu_step(batches[i % 2], c)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cpu_step(batches[i % 2], c)
+    dt = time.perf_counter() - t0
+    return dict(value=steps * c["Na"] / dt, unit=UNIT, cores=cores, kind="port",
+                sample="%d full %s steps (%d segments each) after %d warm-up, oracle/ C+OpenMP NMS "
+                       "tail and RoIAlignAvg + torch-CPU DVSA fwd+bwd, %.2f s" %
+                       (steps, cfg_name, c["Na"], warmup, dt)), dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))  # bounded sample: ~0.5 s of host work per step
+    warm = max(1, min(args.warmup, 2))
+    base, ms = time_cpu(args.cfg, steps, warm)
+    line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=steps,
+                warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32 (fp64 inside RoIAlign interpolation, as the reference)",
+                data="synthetic", impl="reference", config=workload_config(args.cfg, 1),
+                cpu_baseline=base,
+                e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    line["config"]["note"] = ("CPU arm runs one replica on rank 0's host cores regardless of "
+                              "--gpus (world=%d)" % world)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------- GPU arm ----
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        import torch
+        self.proc, self.path = None, "/tmp/nafae_clocks_%d.csv" % os.getpid()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", uuid, "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def algorithmic_bytes(rois, c):
+    """in = min(F*C*H*W*4, sum_r C*4*cells_r) + out + rois, cells_r = distinct
+    feature cells touched by RoI r's 8x8 corner-grid samples."""
+    F = c["Na"] * c["Ns"]
+    H, W, C = c["H"], c["W"], c["C"]
+    r = rois.reshape(-1, 5).astype(np.float64)
+    s = 1.0 / 16.0
+    cells = 0
+    for row in r:
+        xs = row[1] * s + np.arange(8) * (max(row[3] * s - row[1] * s + 1, 0) / 7.0)
+        ys = row[2] * s + np.arange(8) * (max(row[4] * s - row[2] * s + 1, 0) / 7.0)
+        xs = xs[(xs >= 0) & (xs < W)]
+        ys = ys[(ys >= 0) & (ys < H)]
+        cx = np.minimum(np.floor(xs), W - 2)
+        cy = np.minimum(np.floor(ys), H - 2)
+        cells += len(np.unique(np.concatenate([cx, cx + 1]))) * len(np.unique(np.concatenate([cy, cy + 1])))
+    full = F * C * H * W * 4
+    inp = min(full, cells * C * 4)
+    out = r.shape[0] * C * 49 * 4
+    return dict(total=inp + out + r.shape[0] * 20, inp=inp, out=out, full_map=full)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nafae_b200 import synth, parallel
+    from nafae_b200.pipeline import GroundingStep
+
+    rank, world, local = parallel.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    c = synth.CONFIGS[args.cfg]
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    def make_step():
+        return GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], c["C"], c["H"], c["W"], c["n"],
+                             pre_nms_topn=c["pre"], Delta=c["Delta"], vis_lam=c["vis_lam"],
+                             train=c["train"], device=dev)
+
+    host = [synth.make_batch(args.cfg, 1234 + 10 * rank + i) for i in range(2)]
+    steps = [make_step() for _ in range(2)]
+    # DP: the gradient all-reduce runs over a flat bucket sized like the reference's trainable
+    # parameters; this path's dL/dword_feats is written straight into it
+    buckets = None
+    if world > 1:
+        buckets = [parallel.GradBucket(parallel.trainable_grad_elems(), dev, world) for _ in range(2)]
+        for st, b in zip(steps, buckets):
+            st.grad_word = b.views([(st.NQ, c["D"])])[0]
+    for st, hb in zip(steps, host):
+        st.load(hb)
+        st.capture()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def loop(n):
+        for i in range(n):
+            j = i & 1
+            if buckets:
+                buckets[j].wait()
+            steps[j].replay()
+            if buckets:
+                buckets[j].allreduce_async()
+        if buckets:
+            for b in buckets:
+                b.wait()
+
+    loop(Wm)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loop(K)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * K * c["Na"] / (ms_total / 1e3)
+
+    # dominant kernel alone, same stream, same alternating inputs (roofline.achieved)
+    from nafae_b200 import _C
+
+    def align_only(st):
+        _C.check(_C.lib.nafae_roi_align_forward(_C.ptr(st.features), st.scale, st.F, st.R, st.H, st.W,
+                                                st.C, 7, 7, _C.POOL_AVG, _C.ptr(st.rois),
+                                                _C.ptr(st.pooled), 0, None, 0, _C.stream(dev)),
+                 "nafae_roi_align_forward")
+    for i in range(Wm):
+        align_only(steps[i & 1])
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(K):
+        align_only(steps[i & 1])
+    k1.record()
+    torch.cuda.synchronize()
+    kern_us = k0.elapsed_time(k1) / K * 1e3
+    clocks = sampler.stop() if sampler else None
+
+    # end to end through the public API with HOST (pinned) buffers, H2D + D2H inside the timing
+    e2e = None
+    if not args.no_e2e:
+        pinned = []
+        for hb in host:
+            pb = {}
+            for k, v in hb.items():
+                t = torch.tensor(v, dtype=torch.int32) if k == "lens" else torch.from_numpy(v)
+                pb[k] = t.pin_memory()
+            pinned.append(pb)
+        res = [dict(loss=torch.zeros((), dtype=torch.float32).pin_memory(),
+                    D_ind=torch.zeros((steps[0].F, steps[0].NQ), dtype=torch.int64).pin_memory())
+               for _ in range(2)]
+        copy_s = torch.cuda.Stream(dev)
+        comp = torch.cuda.current_stream()
+        loaded = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        for ev in free:
+            ev.record()
+        Ke = max(10, min(K, 50))
+
+        def e2e_loop(n):
+            for i in range(n):
+                j = i & 1
+                with torch.cuda.stream(copy_s):
+                    copy_s.wait_event(free[j])
+                    steps[j].load(pinned[j], non_blocking=True)
+                    loaded[j].record(copy_s)
+                comp.wait_event(loaded[j])
+                steps[j].replay()
+                res[j]["loss"].copy_(steps[j].loss, non_blocking=True)
+                res[j]["D_ind"].copy_(steps[j].D_ind, non_blocking=True)
+                free[j].record(comp)
+        e2e_loop(4)
+        barrier()
+        t0 = time.perf_counter()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        e2e_loop(Ke)
+        s1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ems = torch.tensor([max(s0.elapsed_time(s1), 0.0)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = dict(value=world * Ke * c["Na"] / (float(ems.item()) / 1e3), unit=UNIT,
+                   h2d_bytes_per_step=int(steps[0].h2d_bytes()),
+                   d2h_bytes_per_step=int(4 + steps[0].F * steps[0].NQ * 8),
+                   steps=Ke, ms_per_step=float(ems.item()) / Ke, wall_ms_per_step=wall / Ke * 1e3,
+                   api="GroundingStep.load(pinned host batch) + replay() + loss/D_ind D2H, "
+                       "copy and compute streams double-buffered")
+
+    if rank != 0:
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    ab = algorithmic_bytes(steps[0].rois.cpu().numpy(), c)
+    achieved = ab["total"] / (kern_us * 1e-6) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.cfg, {}).get("align_pool_fwd_slab_dram_bytes")
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=Wm,
+                ms_per_step=ms_total / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", config=workload_config(args.cfg, world),
+                gpu_launches=K * steps[0].kernels_per_step(),
+                roofline=dict(bound="hbm", kernel="align_pool_fwd_slab", achieved=achieved, peak=peak,
+                              unit="GB/s", frac=achieved / peak, traffic=traffic,
+                              kernel_us=kern_us, algorithmic_bytes=ab["total"], peak_source=peak_src,
+                              step_frac=(ab["total"] / (ms_total / K * 1e-3) / 1e9) / peak),
+                clocks=clocks)
+    if world > 1:
+        line["config"]["allreduce"] = ("NCCL all-reduce SUM/world per step over a flat fp32 bucket of "
+                                       "%d elems on a side stream, overlapped with the next step"
+                                       % parallel.trainable_grad_elems())
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        base, _ = time_cpu(args.cfg, 5, 1)
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

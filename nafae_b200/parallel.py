@@ -1,0 +1,92 @@
+"""Data-parallel plumbing: one process per GPU, torch.distributed (NCCL over NVLink 5 / NVSwitch).
+
+Video segments shard across ranks with no forward exchange; the only collective
+of a training step is one all-reduce (SUM, then /world) over a flat fp32 bucket of the trainable
+gradients -- vis_ebd.fc1 (512x4096+512), word_ebd.fc1 (512xglove+512), word_ebd.bn (2x512): 2.20 M
+floats = 8.8 MB at glove_dim 200 (reference model.py:616-642, optimiser at model.py:1030-1036).
+The all-reduce is issued on a side stream so it overlaps the next step's NMS / RoIAlign, which do
+not depend on gradients.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def trainable_grad_elems(vis_fc_dim=4096, glove_dim=200, ebd_dim=512):
+    return (ebd_dim * vis_fc_dim + ebd_dim) + (ebd_dim * glove_dim + ebd_dim) + 2 * ebd_dim
+
+
+def init_from_env(backend=None):
+    """Join the process group torchrun describes; returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local
+
+
+def shard_segments(num_segments, rank, world):
+    """Contiguous shard [begin, end) of the segment list for `rank` (frames of a segment are never
+    split across ranks)."""
+    base, rem = divmod(num_segments, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class GradBucket(object):
+    """Flat fp32 gradient bucket with an overlapped all-reduce.
+
+    ``views(shapes)`` hands out non-overlapping views for the parameter gradients; ``allreduce_async``
+    launches SUM/world on a side stream after the producing stream's current work; ``wait`` makes the
+    consuming stream wait for it (no host sync on either side).
+    """
+
+    def __init__(self, numel, device, world=None):
+        self.buf = torch.zeros((numel,), dtype=torch.float32, device=device)
+        self.world = world if world is not None else (dist.get_world_size()
+                                                      if dist.is_initialized() else 1)
+        self.stream = torch.cuda.Stream(device) if self.buf.is_cuda else None
+        self._done = None
+
+    def views(self, shapes):
+        out, off = [], 0
+        for shp in shapes:
+            n = 1
+            for s in shp:
+                n *= int(s)
+            out.append(self.buf[off:off + n].view(*shp))
+            off += n
+        if off > self.buf.numel():
+            raise ValueError("bucket too small")
+        return out
+
+    def allreduce_async(self):
+        if self.world <= 1:
+            return
+        if self.stream is None:  # CPU / gloo (tests)
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
+            self.buf.div_(self.world)
+            return
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
+            self.buf.div_(self.world)
+            self._done = torch.cuda.Event()
+            self._done.record()
+
+    def wait(self):
+        if self._done is not None:
+            torch.cuda.current_stream().wait_event(self._done)
+            self._done = None

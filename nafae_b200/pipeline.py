@@ -1,0 +1,116 @@
+"""Pre-allocated, graph-capturable execution of the whole hot path for one batch of segments:
+
+    proposal tail (batched NMS + top-N + padding)  ->  RoIAlignAvg 7x7  ->  [bridge: caller's
+    PyTorch]  ->  similarity + losses forward  ->  backward (dL/dvis_feats, dL/dword_feats)
+
+``GroundingStep`` is the public fast path: every buffer is allocated once, every kernel is
+launched through the C ABI on the current stream with no host synchronisation, so ``run()`` can be
+captured into a CUDA graph (``capture()`` / ``replay()``).  The module classes in ``nafae_b200.model``
+and ``nafae_b200.grounding`` are the drop-in, autograd-friendly form of the same kernels.
+"""
+import torch
+
+from . import _C
+
+
+class GroundingStep(object):
+    KERNELS_PER_STEP_TRAIN = 5  # proposal_tail, align_pool_fwd_slab, ground_fwd, bwd_cluster, bwd_main
+    KERNELS_PER_STEP_EVAL = 3
+
+    def __init__(self, Na, Ns, Nb, Ne, D, C, H, W, n_props, pre_nms_topn=6000, nms_thresh=0.7,
+                 spatial_scale=1.0 / 16.0, Delta=10.0, vis_lam=4.13, train=True, device=None):
+        self.dev = torch.device(device if device is not None else
+                                "cuda:%d" % torch.cuda.current_device())
+        self.dims = (Na, Ns, Nb, Ne, D)
+        self.F, self.R, self.NQ = Na * Ns, Na * Ns * Nb, Na * Ne
+        self.C, self.H, self.W, self.n = C, H, W, n_props
+        self.pre, self.thresh, self.scale = int(pre_nms_topn), float(nms_thresh), float(spatial_scale)
+        self.Delta, self.vis_lam, self.train = float(Delta), float(vis_lam), bool(train)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        # device-resident inputs
+        self.features = torch.empty((self.F, C, H, W), **f32)
+        self.proposals = torch.empty((self.F, n_props, 4), **f32)
+        self.scores = torch.empty((self.F, n_props), **f32)
+        self.vis_feats = torch.empty((self.R, D), **f32)
+        self.word_feats = torch.empty((self.NQ, D), **f32)
+        self.lens = torch.zeros((Na,), dtype=torch.int32, device=self.dev)
+        # outputs
+        self.rois = torch.empty((self.F, Nb, 5), **f32)
+        self.roi_scores = torch.empty((self.F, Nb), **f32)
+        self.pooled = torch.empty((self.R, C, 7, 7), **f32)
+        self.D_ind = torch.empty((self.F, self.NQ), dtype=torch.int64, device=self.dev)
+        self.D_sim = torch.empty((self.F, self.NQ), **f32)
+        self.loss = torch.zeros((), **f32)
+        self.grad_loss = torch.ones((), **f32)
+        self.grad_vis = torch.empty((self.R, D), **f32)
+        self.grad_word = torch.empty((self.NQ, D), **f32)
+        nbytes = int(_C.lib.nafae_ground_workspace_bytes(*self.dims))
+        self.ws = torch.zeros((nbytes // 4,), dtype=torch.int32, device=self.dev)
+        self.graph = None
+
+    # -- input staging ---------------------------------------------------------------------
+    def load(self, batch, non_blocking=False):
+        """Copy a host batch (dict of numpy arrays / CPU tensors as made by synth.make_batch) in."""
+        def put(dst, src):
+            t = src if torch.is_tensor(src) else torch.from_numpy(src)
+            dst.copy_(t.view(dst.shape), non_blocking=non_blocking)
+        put(self.features, batch["features"])
+        put(self.proposals, batch["proposals"])
+        put(self.scores, batch["scores"])
+        put(self.vis_feats, batch["vis_feats"])
+        put(self.word_feats, batch["word_feats"])
+        lens = batch["lens"]
+        if not torch.is_tensor(lens):
+            lens = torch.tensor([int(x) for x in lens], dtype=torch.int32)
+        self.lens.copy_(lens.to(torch.int32), non_blocking=non_blocking)
+
+    def h2d_bytes(self):
+        return sum(t.numel() * t.element_size() for t in
+                   (self.features, self.proposals, self.scores, self.vis_feats, self.word_feats,
+                    self.lens))
+
+    # -- the step --------------------------------------------------------------------------
+    def run(self, backward=None):
+        """Enqueue the whole step on the current stream.  No host sync, no allocation."""
+        Na, Ns, Nb, Ne, D = self.dims
+        L, P = _C.lib, _C.ptr
+        s = _C.stream(self.dev)
+        do_bwd = self.train if backward is None else backward
+        with torch.cuda.device(self.dev):
+            _C.check(L.nafae_proposal_tail(P(self.proposals), P(self.scores), self.F, self.n,
+                                           self.pre, Nb, self.thresh, P(self.rois),
+                                           P(self.roi_scores), None, s), "nafae_proposal_tail")
+            _C.check(L.nafae_roi_align_forward(P(self.features), self.scale, self.F, self.R, self.H,
+                                               self.W, self.C, 7, 7, _C.POOL_AVG, P(self.rois),
+                                               P(self.pooled), 0, None, 0, s),
+                     "nafae_roi_align_forward")
+            # (bridge: fc6/fc7 + VisEbd / WordEbd run here in the caller's PyTorch code and
+            #  produce vis_feats / word_feats; they are outside this path)
+            _C.check(L.nafae_ground_forward(P(self.vis_feats), P(self.word_feats), P(self.lens),
+                                            Na, Ns, Nb, Ne, D, self.Delta, self.vis_lam,
+                                            int(self.train), P(self.D_ind), P(self.D_sim),
+                                            P(self.loss), P(self.ws), self.ws.numel() * 4, s),
+                     "nafae_ground_forward")
+            if do_bwd:
+                _C.check(L.nafae_ground_backward(P(self.grad_loss), P(self.vis_feats),
+                                                 P(self.word_feats), P(self.lens), Na, Ns, Nb, Ne,
+                                                 D, self.Delta, self.vis_lam, int(self.train),
+                                                 P(self.D_ind), P(self.D_sim), P(self.grad_vis),
+                                                 P(self.grad_word), P(self.ws),
+                                                 self.ws.numel() * 4, s), "nafae_ground_backward")
+
+    def kernels_per_step(self):
+        return self.KERNELS_PER_STEP_TRAIN if self.train else self.KERNELS_PER_STEP_EVAL
+
+    def capture(self):
+        """Capture run() into a CUDA graph (launch-bound at this size: 5 kernels, ~100 us)."""
+        self.run()  # warm up (sets func attributes, loads modules) outside capture
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self.graph = g
+        return g
+
+    def replay(self):
+        self.graph.replay()
