@@ -85,33 +85,30 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Warp-cooperative dot product of two global rows with the loads issued in independent batches
+// of 8 per lane (a plain k-loop with a runtime trip count serialises on L2 latency).
+__device__ __forceinline__ float warp_dot(const float* __restrict__ x, const float* __restrict__ y,
+                                          int D, int lane) {
+  float acc = 0.f;
+  for (int k0 = 0; k0 < D; k0 += 256) {
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + lane + 32 * j;
+      a[j] = k < D ? __ldg(x + k) : 0.f;
+      b[j] = k < D ? __ldg(y + k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(a[j], b[j], acc);
+  }
+  return warp_sum(acc);
+}
+
 // per-column frame statistics over the Ns frames of one segment (model.py:583-588)
 struct ColStat {
   float mn, mx, den;
   int s_mn, s_mx;  // first index of the minimum / maximum (torch.min/max(dim) tie rule)
 };
-
-__device__ __forceinline__ ColStat col_stat(const float* __restrict__ Dsim, int a, int c,
-                                            const Dims& d) {
-  ColStat st;
-  st.mn = INFINITY;
-  st.mx = -INFINITY;
-  st.s_mn = 0;
-  st.s_mx = 0;
-  for (int s = 0; s < d.Ns; ++s) {
-    const float x = __ldcg(Dsim + (size_t)(a * d.Ns + s) * d.NQ + c);
-    if (x < st.mn) {
-      st.mn = x;
-      st.s_mn = s;
-    }
-    if (x > st.mx) {
-      st.mx = x;
-      st.s_mx = s;
-    }
-  }
-  st.den = (st.mx - st.mn) + kEps;
-  return st;
-}
 
 // ------------------------------------------------------------------------ forward ----
 struct FwdParams {
@@ -173,19 +170,23 @@ __global__ void __launch_bounds__(kFwdThreads) ground_fwd_kernel(const FwdParams
   int best_r = 0;
   const float* vis_f = p.vis + (size_t)f * d.Nb * d.D;
 
+  __shared__ __align__(8) uint64_t s_bar;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  uint32_t parity = 0;
   for (int r0 = 0; r0 < d.Nb; r0 += kRowTile) {
     const int rows = min(kRowTile, d.Nb - r0);
-    __syncthreads();
-    {  // stage the row tile (coalesced float4)
-      const float4* src = reinterpret_cast<const float4*>(vis_f + (size_t)r0 * d.D);
-      float4* dst = reinterpret_cast<float4*>(sm);
-      const int n4 = rows * d.D / 4;
-      for (int i = tid; i < n4; i += kFwdThreads) dst[i] = __ldg(src + i);
+    __syncthreads();  // previous tile consumed (and the barrier init is visible)
+    if (tid == 0) {   // one bulk async copy (TMA engine) stages the whole row tile
+      const uint32_t bytes = (uint32_t)rows * d.D * 4u;
+      mbar_arrive_expect_tx(&s_bar, bytes);
+      bulk_g2s(sm, vis_f + (size_t)r0 * d.D, bytes, &s_bar);
     }
-    __syncthreads();
-    if (!any_live) continue;
+    bool waited = false;
     for (int k0 = 0; k0 < d.D; k0 += 32 * kKS) {
-      // this chunk's word slices for the warp's 4 columns
+      // this chunk's word slices for the warp's 4 columns (overlaps the tile copy)
       float wv[4][kKS];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -196,6 +197,12 @@ __global__ void __launch_bounds__(kFwdThreads) ground_fwd_kernel(const FwdParams
           wv[j][i] = (live[j] && k0 + k < d.D) ? __ldg(wr + k) : 0.f;
         }
       }
+      if (!waited) {
+        mbar_wait(&s_bar, parity);
+        parity ^= 1u;
+        waited = true;
+      }
+      if (!any_live) break;
       const bool last_chunk = k0 + 32 * kKS >= d.D;
       for (int r = 0; r < rows; ++r) {
         const float* vr = sm + (size_t)r * d.D + k0;
@@ -259,20 +266,65 @@ __global__ void __launch_bounds__(kFwdThreads) ground_fwd_kernel(const FwdParams
   if (tid == 0) *w.done_cnt = 0;
 }
 
-// P2: frame attention + Sf for segment a; clustering partials (train)
+// Column statistics of one segment from a shared-memory copy of its D_sim block.
+// Sblk is [Ns][NQ]; first-index tie rule like torch.min/max(dim).
+__device__ __forceinline__ ColStat col_stat_smem(const float* __restrict__ Sblk, int c, int Ns,
+                                                 int NQ) {
+  ColStat st;
+  st.mn = INFINITY;
+  st.mx = -INFINITY;
+  st.s_mn = 0;
+  st.s_mx = 0;
+  for (int s = 0; s < Ns; ++s) {
+    const float x = Sblk[s * NQ + c];
+    if (x < st.mn) {
+      st.mn = x;
+      st.s_mn = s;
+    }
+    if (x > st.mx) {
+      st.mx = x;
+      st.s_mx = s;
+    }
+  }
+  st.den = (st.mx - st.mn) + kEps;
+  return st;
+}
+
+// P2: frame attention + Sf for segment a; clustering partials (train).
+// Everything the phase needs from other CTAs (the segment's Ns x NQ block of D_sim / D_ind) is
+// pulled into shared memory with ONE round of independent L2 loads.
 __device__ void phase2_segment(const FwdParams& p, const Ws& w, int a, float* sm) {
   const Dims& d = p.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // Sf[a,s,a'] = sum_e S*S_att / div[a']   (model.py:589-593); thread per (s, a')
+  const int blk = d.Ns * d.NQ;
+  float* Sblk = sm;                                   // [Ns][NQ]
+  int* Iblk = reinterpret_cast<int*>(sm + blk);       // [Ns][NQ]
+  float* c_mn = sm + 2 * blk;                         // [NQ]
+  float* c_iden = c_mn + d.NQ;                        // [NQ] 1/den
+  float* inv = c_iden + d.NQ;                         // [Ne][Ns] 1/(||x||+eps) of the picked rows
+  __syncthreads();
+  const float* gS = p.D_sim + (size_t)a * blk;
+  const long long* gI = p.D_ind + (size_t)a * blk;
+  for (int i = tid; i < blk; i += kFwdThreads) {
+    Sblk[i] = __ldcg(gS + i);
+    Iblk[i] = (int)__ldcg(gI + i);
+  }
+  __syncthreads();
+  for (int c = tid; c < d.NQ; c += kFwdThreads) {
+    const ColStat st = col_stat_smem(Sblk, c, d.Ns, d.NQ);
+    c_mn[c] = st.mn;
+    c_iden[c] = 1.f / st.den;
+  }
+  __syncthreads();
+  // Sf[a,s,a'] = sum_e S*S_att / div[a']   (model.py:583-593); thread per (s, a')
   for (int i = tid; i < d.Ns * d.Na; i += kFwdThreads) {
     const int s = i / d.Na, a2 = i % d.Na;
     const int len = __ldg(p.lens + a2);
     float acc = 0.f;
     for (int e = 0; e < len; ++e) {
       const int c = a2 * d.Ne + e;
-      const ColStat st = col_stat(p.D_sim, a, c, d);
-      const float x = __ldcg(p.D_sim + (size_t)(a * d.Ns + s) * d.NQ + c);
-      acc += x * ((x - st.mn) / st.den);
+      const float x = Sblk[s * d.NQ + c];
+      acc += x * ((x - c_mn[c]) * c_iden[c]);
     }
     w.Sf[((size_t)a * d.Ns + s) * d.Na + a2] = acc / (float)(len == 0 ? 1 : len);
   }
@@ -281,27 +333,10 @@ __device__ void phase2_segment(const FwdParams& p, const Ws& w, int a, float* sm
   // clustering loss of segment a (model.py:553-577).  Rows come from frame 0 of segment 0: the
   // box index is used without its (segment, frame) offset.
   const int len = __ldg(p.lens + a);
-  float* simn = sm;                 // [len][Ns] normalised similarity
-  float* inv = sm + 16 * d.Ns;      // [len][Ns] 1/(||x||+eps)   (Ne <= 16 asserted on host)
-  int* row = reinterpret_cast<int*>(sm + 32 * d.Ns);  // [len][Ns] row index
-  __syncthreads();
-  for (int i = tid; i < len * d.Ns; i += kFwdThreads) {
+  for (int i = warp; i < len * d.Ns; i += kFwdWarps) {  // norms, warp per picked row
     const int e = i / d.Ns, s = i % d.Ns;
-    const int c = a * d.Ne + e;
-    const ColStat st = col_stat(p.D_sim, a, c, d);
-    const float x = __ldcg(p.D_sim + (size_t)(a * d.Ns + s) * d.NQ + c);
-    simn[i] = (x - st.mn) / st.den;
-    row[i] = (int)__ldcg(p.D_ind + (size_t)(a * d.Ns + s) * d.NQ + c);
-  }
-  __syncthreads();
-  for (int i = warp; i < len * d.Ns; i += kFwdWarps) {  // norms, warp per row
-    const float* x = p.vis + (size_t)row[i] * d.D;
-    float acc = 0.f;
-    for (int k = lane; k < d.D; k += 32) {
-      const float v = __ldg(x + k);
-      acc = fmaf(v, v, acc);
-    }
-    acc = warp_sum(acc);
+    const float* x = p.vis + (size_t)Iblk[s * d.NQ + a * d.Ne + e] * d.D;
+    const float acc = warp_dot(x, x, d.D, lane);
     if (lane == 0) inv[i] = 1.f / (sqrtf(acc) + kEps);
   }
   __syncthreads();
@@ -317,13 +352,13 @@ __device__ void phase2_segment(const FwdParams& p, const Ws& w, int a, float* sm
       ++s;
     }
     const int t = s + 1 + q;
-    const float* xs = p.vis + (size_t)row[e * d.Ns + s] * d.D;
-    const float* xt = p.vis + (size_t)row[e * d.Ns + t] * d.D;
-    float acc = 0.f;
-    for (int k = lane; k < d.D; k += 32) acc = fmaf(__ldg(xs + k), __ldg(xt + k), acc);
-    acc = warp_sum(acc);
-    const float dot = acc * (simn[e * d.Ns + s] * inv[e * d.Ns + s]) *
-                      (simn[e * d.Ns + t] * inv[e * d.Ns + t]);
+    const int c = a * d.Ne + e;
+    const float* xs = p.vis + (size_t)Iblk[s * d.NQ + c] * d.D;
+    const float* xt = p.vis + (size_t)Iblk[t * d.NQ + c] * d.D;
+    const float acc = warp_dot(xs, xt, d.D, lane);
+    const float ss = (Sblk[s * d.NQ + c] - c_mn[c]) * c_iden[c];
+    const float st = (Sblk[t * d.NQ + c] - c_mn[c]) * c_iden[c];
+    const float dot = acc * (ss * inv[e * d.Ns + s]) * (st * inv[e * d.Ns + t]);
     const float g = 1.f - dot;
     if (lane == 0) {
       gsum += 2.f * g;
@@ -355,7 +390,13 @@ __device__ void phase3_final(const FwdParams& p, const Ws& w, float* sm) {
   const int tid = threadIdx.x;
   const int n = d.Na * d.Ns * d.Na;
   __shared__ float s_part[kFwdThreads];
-  for (int i = tid; i < n; i += kFwdThreads) w.hgrad[i] = 0.f;
+  float* Sf = sm;       // [Na][Ns][Na]
+  float* hg = sm + n;   // [Na][Ns][Na]
+  __syncthreads();
+  for (int i = tid; i < n; i += kFwdThreads) {
+    Sf[i] = __ldcg(w.Sf + i);
+    hg[i] = 0.f;
+  }
   __syncthreads();
   // frame_score[a,s] = mean_a'' relu(Sf[a'',s,a] - d[a,s] + Delta) + mean_a' relu(Sf[a,s,a'] - d[a,s] + Delta)
   float part = 0.f;
@@ -363,51 +404,54 @@ __device__ void phase3_final(const FwdParams& p, const Ws& w, float* sm) {
   const float gscale = 10.f / (float)(d.Na * d.Ns) * inv_na;  // d(margin)/d(relu term)
   for (int i = tid; i < d.Na * d.Ns; i += kFwdThreads) {
     const int a = i / d.Ns, s = i % d.Ns;
-    const float dg = __ldcg(w.Sf + ((size_t)a * d.Ns + s) * d.Na + a);
+    const float dg = Sf[(a * d.Ns + s) * d.Na + a];
     float t1 = 0.f, t2 = 0.f;
     float gd = 0.f;  // gradient reaching d[a,s]
     for (int o = 0; o < d.Na; ++o) {
-      const float v1 = (__ldcg(w.Sf + ((size_t)o * d.Ns + s) * d.Na + a) - dg) + p.Delta;
-      const float v2 = (__ldcg(w.Sf + ((size_t)a * d.Ns + s) * d.Na + o) - dg) + p.Delta;
+      const float v1 = (Sf[(o * d.Ns + s) * d.Na + a] - dg) + p.Delta;
+      const float v2 = (Sf[(a * d.Ns + s) * d.Na + o] - dg) + p.Delta;
       if (v1 > 0.f) {
         t1 += v1;
-        atomicAdd(w.hgrad + ((size_t)o * d.Ns + s) * d.Na + a, gscale);
+        atomicAdd(hg + (o * d.Ns + s) * d.Na + a, gscale);
         gd -= gscale;
       }
       if (v2 > 0.f) {
         t2 += v2;
-        atomicAdd(w.hgrad + ((size_t)a * d.Ns + s) * d.Na + o, gscale);
+        atomicAdd(hg + (a * d.Ns + s) * d.Na + o, gscale);
         gd -= gscale;
       }
     }
-    atomicAdd(w.hgrad + ((size_t)a * d.Ns + s) * d.Na + a, gd);
+    atomicAdd(hg + (a * d.Ns + s) * d.Na + a, gd);
     part += t1 * inv_na + t2 * inv_na;
   }
   s_part[tid] = part;
   __syncthreads();
-  if (tid == 0) {
-    float fs = 0.f;
-    for (int k = 0; k < kFwdThreads; ++k) fs += s_part[k];
-    const float mean_fs = fs / (float)(d.Na * d.Ns);
-    float loss = mean_fs * 10.f;
-    float vis_loss = 0.f, dem = 0.f;
-    if (p.train) {
-      float ts = 0.f;
-      int tc = 0;
-      for (int a = 0; a < d.Na; ++a) {
-        ts += __ldcg(w.vsum + a);
-        tc += __ldcg(w.vcnt + a);
+  for (int i = tid; i < n; i += kFwdThreads) w.hgrad[i] = hg[i];
+  if (tid < 32) {  // deterministic tree over the 256 partials
+    float v = 0.f;
+    for (int k = tid; k < kFwdThreads; k += 32) v += s_part[k];
+    v = warp_sum(v);
+    if (tid == 0) {
+      const float mean_fs = v / (float)(d.Na * d.Ns);
+      float loss = mean_fs * 10.f;
+      float vis_loss = 0.f, dem = 0.f;
+      if (p.train) {
+        float ts = 0.f;
+        int tc = 0;
+        for (int a = 0; a < d.Na; ++a) {
+          ts += __ldcg(w.vsum + a);
+          tc += __ldcg(w.vcnt + a);
+        }
+        dem = (float)tc;
+        vis_loss = ts / dem;  // NaN when nothing is unmasked, like the reference (model.py:576-577)
+        loss = (mean_fs + p.vis_lam * vis_loss) * 10.f;
       }
-      dem = (float)tc;
-      vis_loss = ts / dem;  // NaN when nothing is unmasked, like the reference (model.py:576-577)
-      loss = (mean_fs + p.vis_lam * vis_loss) * 10.f;
+      w.scal[0] = vis_loss;
+      w.scal[1] = dem;
+      w.scal[2] = mean_fs;
+      *p.loss = loss;
     }
-    w.scal[0] = vis_loss;
-    w.scal[1] = dem;
-    w.scal[2] = mean_fs;
-    *p.loss = loss;
   }
-  (void)sm;
 }
 
 // ----------------------------------------------------------------------- backward ----
@@ -426,34 +470,158 @@ struct BwdParams {
   int train;
 };
 
-// d(margin_loss)/dS[a,s,c] for one column c = (a2, e), all s of segment a (A12 in SURVEY.md).
-// out[s] for s < Ns; x = S[a,:,c].
-__device__ __forceinline__ void col_grad(const BwdParams& p, const Ws& w, int a, int c, float gout,
-                                         float* __restrict__ out) {
-  const Dims& d = p.d;
-  const int a2 = c / d.Ne;
-  const int len = __ldg(p.lens + a2);
-  const ColStat st = col_stat(p.D_sim, a, c, d);
-  const float inv_div = 1.f / (float)(len == 0 ? 1 : len);
-  const float inv_den = 1.f / st.den;
-  float g_mn = 0.f, g_mx = 0.f;
-  for (int s = 0; s < d.Ns; ++s) {
-    const float x = __ldg(p.D_sim + (size_t)(a * d.Ns + s) * d.NQ + c);
-    const float q = gout * __ldg(w.hgrad + ((size_t)a * d.Ns + s) * d.Na + a2) * inv_div;
-    const float att = (x - st.mn) * inv_den;
-    out[s] = q * (att + x * inv_den);
-    const float qx = q * x * inv_den * inv_den;
-    g_mn += qx * ((x - st.mx) - kEps);
-    g_mx -= qx * (x - st.mn);
-  }
-  out[st.s_mn] += g_mn;
-  out[st.s_mx] += g_mx;
-}
-
 constexpr int kBwdThreads = 256;
 constexpr int kMaxNsLocal = 64;  // frames per segment handled by the fused backward
 
-// clustering-loss gradient -> ws.clus[Nb][D] (atomic accumulate); grid NQ, CTA per (a, e)
+// d(margin_loss)/dS[a,s,c] for all s of one (segment, column), from shared-memory copies:
+// x[s*xs] = S[a,s,c], h[s*hs] = d(margin)/dSf[a,s,a2] (A12 in SURVEY.md).  out[s*os].
+__device__ __forceinline__ void col_grad_smem(const float* __restrict__ x, int xs,
+                                              const float* __restrict__ h, int hs, int Ns,
+                                              float scale /* gout / div */, float* out, int os) {
+  float mn = INFINITY, mx = -INFINITY;
+  int s_mn = 0, s_mx = 0;
+  for (int s = 0; s < Ns; ++s) {
+    const float v = x[s * xs];
+    if (v < mn) {
+      mn = v;
+      s_mn = s;
+    }
+    if (v > mx) {
+      mx = v;
+      s_mx = s;
+    }
+  }
+  const float iden = 1.f / ((mx - mn) + kEps);
+  float g_mn = 0.f, g_mx = 0.f;
+  for (int s = 0; s < Ns; ++s) {
+    const float v = x[s * xs];
+    const float q = scale * h[s * hs];
+    out[s * os] = q * ((v - mn) * iden + v * iden);
+    const float qx = q * v * iden * iden;
+    g_mn += qx * ((v - mx) - kEps);
+    g_mx -= qx * (v - mn);
+  }
+  out[s_mn * os] += g_mn;
+  out[s_mx * os] += g_mx;
+}
+
+// grid F + NQ.  blockIdx < F: dL/dvis rows of frame f (dense overwrite, Nb x D).
+//               else        : dL/dword row of column c.
+// Every cross-CTA input is staged into shared memory with one round of independent loads; the
+// gather loops issue their global loads in batches so they overlap instead of serialising.
+__global__ void __launch_bounds__(kBwdThreads) ground_bwd_main_kernel(const BwdParams p) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ int s_nlive;
+  const Dims& d = p.d;
+  const Ws w = ws_carve(p.ws, d);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const float gout = __ldg(p.gout);
+  if ((int)blockIdx.x < d.F) {
+    const int f = blockIdx.x, a = f / d.Ns, s_me = f % d.Ns;
+    const int blk = d.Ns * d.NQ;
+    float* Sblk = sm;                                  // [Ns][NQ]
+    float* hg = Sblk + blk;                            // [Ns][Na]
+    float* gtmp = hg + d.Ns * d.Na;                    // [Ns][NQ] per-column gradients
+    int* ridx = reinterpret_cast<int*>(gtmp + blk);    // [NQ]
+    int* live = ridx + d.NQ;                           // [NQ] compact list of live columns
+    // [kRowTile][D], 16-byte aligned for the float4 write-out
+    float* acc = sm + ((2 * (size_t)blk + (size_t)d.Ns * d.Na + 2 * (size_t)d.NQ + 3) & ~(size_t)3);
+    for (int i = tid; i < blk; i += kBwdThreads) Sblk[i] = __ldg(p.D_sim + (size_t)a * blk + i);
+    for (int i = tid; i < d.Ns * d.Na; i += kBwdThreads)
+      hg[i] = __ldg(w.hgrad + (size_t)a * d.Ns * d.Na + i);
+    for (int c = tid; c < d.NQ; c += kBwdThreads) {
+      const bool lv = (c % d.Ne) < __ldg(p.lens + c / d.Ne);
+      ridx[c] = lv ? (int)__ldg(p.D_ind + (size_t)f * d.NQ + c) : -1;
+    }
+    __syncthreads();
+    for (int c = tid; c < d.NQ; c += kBwdThreads) {
+      if (ridx[c] >= 0) {
+        const int a2 = c / d.Ne;
+        const int len = __ldg(p.lens + a2);
+        col_grad_smem(Sblk + c, d.NQ, hg + a2, d.Na, d.Ns, gout / (float)(len == 0 ? 1 : len),
+                      gtmp + c, d.NQ);
+      }
+    }
+    if (tid < 32) {  // ordered compaction of the live columns (warp 0)
+      int n = 0;
+      for (int c0 = 0; c0 < d.NQ; c0 += 32) {
+        const int c = c0 + lane;
+        const bool lv = c < d.NQ && ridx[c] >= 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, lv);
+        if (lv) live[n + __popc(bal & ((1u << lane) - 1u))] = c;
+        n += __popc(bal);
+      }
+      if (lane == 0) s_nlive = n;
+    }
+    __syncthreads();
+    const int nlive = s_nlive;
+    const float* g = gtmp + s_me * d.NQ;
+    for (int r0 = 0; r0 < d.Nb; r0 += kRowTile) {
+      const int rows = min(kRowTile, d.Nb - r0);
+      for (int i = tid; i < rows * d.D; i += kBwdThreads) acc[i] = 0.f;
+      __syncthreads();
+      for (int k = tid; k < d.D; k += kBwdThreads) {  // thread owns feature k of every row
+        for (int j0 = 0; j0 < nlive; j0 += 8) {
+          float wv[8];
+          int rr[8];
+          float gg[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = live[min(j0 + j, nlive - 1)];
+            rr[j] = (j0 + j < nlive) ? ridx[c] - r0 : -1;
+            gg[j] = g[c];
+            wv[j] = __ldg(p.word + (size_t)c * d.D + k);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (rr[j] >= 0 && rr[j] < rows) acc[rr[j] * d.D + k] = fmaf(gg[j], wv[j], acc[rr[j] * d.D + k]);
+        }
+      }
+      __syncthreads();
+      float4* dst = reinterpret_cast<float4*>(p.gvis + ((size_t)f * d.Nb + r0) * d.D);
+      const float4* src = reinterpret_cast<const float4*>(acc);
+      for (int i = tid; i < rows * d.D / 4; i += kBwdThreads) dst[i] = src[i];
+      __syncthreads();
+    }
+  } else {
+    const int c = blockIdx.x - d.F, a2 = c / d.Ne;
+    float* dst = p.gword + (size_t)c * d.D;
+    const int len = __ldg(p.lens + a2);
+    if ((c % d.Ne) >= len) {
+      for (int k = tid; k < d.D; k += kBwdThreads) dst[k] = 0.f;
+      return;
+    }
+    float* xcol = sm;                                  // [F]
+    float* hcol = xcol + d.F;                          // [F]
+    float* g = hcol + d.F;                             // [F]
+    int* ridx = reinterpret_cast<int*>(g + d.F);       // [F] global vis row of the picked box
+    for (int f = tid; f < d.F; f += kBwdThreads) {
+      xcol[f] = __ldg(p.D_sim + (size_t)f * d.NQ + c);
+      hcol[f] = __ldg(w.hgrad + (size_t)f * d.Na + a2);
+      ridx[f] = f * d.Nb + (int)__ldg(p.D_ind + (size_t)f * d.NQ + c);
+    }
+    __syncthreads();
+    for (int a = tid; a < d.Na; a += kBwdThreads)
+      col_grad_smem(xcol + a * d.Ns, 1, hcol + a * d.Ns, 1, d.Ns, gout / (float)len, g + a * d.Ns, 1);
+    __syncthreads();
+    for (int k = tid; k < d.D; k += kBwdThreads) {
+      float accv = 0.f;
+      for (int f0 = 0; f0 < d.F; f0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.vis + (size_t)ridx[min(f0 + j, d.F - 1)] * d.D + k);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (f0 + j < d.F) accv = fmaf(g[f0 + j], v[j], accv);
+      }
+      dst[k] = accv;
+    }
+  }
+}
+
+// Clustering-loss gradient, launched AFTER ground_bwd_main_kernel: adds into grad_vis rows
+// 0..Nb-1 (the rows the reference's un-offset index_select gathers).
+// grid NQ, CTA per (a, e); masked entities exit immediately.
 __global__ void __launch_bounds__(kBwdThreads) ground_bwd_cluster_kernel(const BwdParams p) {
   extern __shared__ __align__(16) float sm[];  // Vsum[D] | simn[Ns] | inv[Ns] | dots[Ns] | row[Ns]
   const Dims& d = p.d;
@@ -468,29 +636,35 @@ __global__ void __launch_bounds__(kBwdThreads) ground_bwd_cluster_kernel(const B
   float* inv = simn + d.Ns;
   float* dots = inv + d.Ns;
   int* row = reinterpret_cast<int*>(dots + d.Ns);
-  if (tid == 0) {
-    const ColStat st = col_stat(p.D_sim, a, c, d);
-    for (int s = 0; s < d.Ns; ++s) {
-      const float x = __ldg(p.D_sim + (size_t)(a * d.Ns + s) * d.NQ + c);
-      simn[s] = (x - st.mn) / st.den;
-      row[s] = (int)__ldg(p.D_ind + (size_t)(a * d.Ns + s) * d.NQ + c);
-    }
+  for (int s = tid; s < d.Ns; s += kBwdThreads) {
+    simn[s] = __ldg(p.D_sim + (size_t)(a * d.Ns + s) * d.NQ + c);
+    row[s] = (int)__ldg(p.D_ind + (size_t)(a * d.Ns + s) * d.NQ + c);
   }
   __syncthreads();
+  float mn = INFINITY, mx = -INFINITY;
+  for (int s = 0; s < d.Ns; ++s) {
+    mn = fminf(mn, simn[s]);
+    mx = fmaxf(mx, simn[s]);
+  }
+  const float iden = 1.f / ((mx - mn) + kEps);
+  __syncthreads();
+  for (int s = tid; s < d.Ns; s += kBwdThreads) simn[s] = (simn[s] - mn) * iden;
   for (int s = warp; s < d.Ns; s += kBwdThreads / 32) {
     const float* x = p.vis + (size_t)row[s] * d.D;
-    float acc = 0.f;
-    for (int k = lane; k < d.D; k += 32) {
-      const float v = __ldg(x + k);
-      acc = fmaf(v, v, acc);
-    }
-    acc = warp_sum(acc);
+    const float acc = warp_dot(x, x, d.D, lane);
     if (lane == 0) inv[s] = 1.f / (sqrtf(acc) + kEps);
   }
   __syncthreads();
   for (int k = tid; k < d.D; k += kBwdThreads) {
     float acc = 0.f;
-    for (int s = 0; s < d.Ns; ++s) acc += simn[s] * inv[s] * __ldg(p.vis + (size_t)row[s] * d.D + k);
+    for (int s0 = 0; s0 < d.Ns; s0 += 8) {
+      float xv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[j] = __ldg(p.vis + (size_t)row[min(s0 + j, d.Ns - 1)] * d.D + k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (s0 + j < d.Ns) acc += simn[s0 + j] * inv[s0 + j] * xv[j];
+    }
     Vsum[k] = acc;
   }
   __syncthreads();
@@ -500,101 +674,40 @@ __global__ void __launch_bounds__(kBwdThreads) ground_bwd_cluster_kernel(const B
     const float* x = p.vis + (size_t)row[s] * d.D;
     const float sc = simn[s] * inv[s];
     float acc = 0.f;
-    for (int k = lane; k < d.D; k += 32) {
-      const float xv = __ldg(x + k);
-      acc = fmaf(xv, Vsum[k] - sc * xv, acc);
+    for (int k0 = 0; k0 < d.D; k0 += 256) {
+      float xv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + lane + 32 * j;
+        xv[j] = k < d.D ? __ldg(x + k) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + lane + 32 * j;
+        if (k < d.D) acc = fmaf(xv[j], Vsum[k] - sc * xv[j], acc);
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) dots[s] = acc * simn[s] * coef;
   }
   __syncthreads();
-  for (int s = 0; s < d.Ns; ++s) {
-    const float* x = p.vis + (size_t)row[s] * d.D;
-    const float iv = inv[s];           // 1/(n+eps)
-    const float nrm = 1.f / iv - kEps; // n
-    const float sc = simn[s] * iv;
-    // dL/dx = gu/(n+eps) - x (x.gu) / (n (n+eps)^2);  gu = simn*coef*(Vsum - V_s)
-    const float c2 = nrm > 0.f ? dots[s] * iv * iv / nrm : 0.f;
-    float* dst = w.clus + (size_t)row[s] * d.D;
-    for (int k = tid; k < d.D; k += kBwdThreads) {
-      const float xv = __ldg(x + k);
-      const float gu = simn[s] * coef * (Vsum[k] - sc * xv);
-      atomicAdd(dst + k, gu * iv - xv * c2);
-    }
-  }
-}
-
-// grid F + NQ.  blockIdx < F: dL/dvis rows of frame f (dense overwrite, Nb x D).
-//               else        : dL/dword row of column c.
-__global__ void __launch_bounds__(kBwdThreads) ground_bwd_main_kernel(const BwdParams p) {
-  extern __shared__ __align__(16) float sm[];
-  const Dims& d = p.d;
-  const Ws w = ws_carve(p.ws, d);
-  const int tid = threadIdx.x;
-  const float gout = __ldg(p.gout);
-  if ((int)blockIdx.x < d.F) {
-    const int f = blockIdx.x, a = f / d.Ns, s_me = f % d.Ns;
-    float* g = sm;                                   // [NQ]
-    int* ridx = reinterpret_cast<int*>(sm + d.NQ);   // [NQ]
-    float* acc = sm + 2 * d.NQ;                      // [kRowTile][D]
-    for (int c = tid; c < d.NQ; c += kBwdThreads) {
-      float gs = 0.f;
-      const bool live = (c % d.Ne) < __ldg(p.lens + c / d.Ne);
-      if (live) {
-        float tmp[kMaxNsLocal];
-        col_grad(p, w, a, c, gout, tmp);
-        gs = tmp[s_me];
+  for (int k = tid; k < d.D; k += kBwdThreads) {
+    for (int s0 = 0; s0 < d.Ns; s0 += 8) {
+      float xs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xs[j] = __ldg(p.vis + (size_t)row[min(s0 + j, d.Ns - 1)] * d.D + k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int s = s0 + j;
+        if (s >= d.Ns) break;
+        const float iv = inv[s];             // 1/(n+eps)
+        const float nrm = 1.f / iv - kEps;   // n
+        const float sc = simn[s] * iv;
+        // dL/dx = gu/(n+eps) - x (x.gu) / (n (n+eps)^2);  gu = simn*coef*(Vsum - V_s)
+        const float c2 = nrm > 0.f ? dots[s] * iv * iv / nrm : 0.f;
+        const float gu = simn[s] * coef * (Vsum[k] - sc * xs[j]);
+        atomicAdd(p.gvis + (size_t)row[s] * d.D + k, gu * iv - xs[j] * c2);
       }
-      g[c] = gs;
-      ridx[c] = live ? (int)__ldg(p.D_ind + (size_t)f * d.NQ + c) : -1;
-    }
-    __syncthreads();
-    for (int r0 = 0; r0 < d.Nb; r0 += kRowTile) {
-      const int rows = min(kRowTile, d.Nb - r0);
-      for (int i = tid; i < rows * d.D; i += kBwdThreads) acc[i] = 0.f;
-      __syncthreads();
-      for (int k = tid; k < d.D; k += kBwdThreads) {  // thread owns feature k of every row
-        for (int c = 0; c < d.NQ; ++c) {
-          const int r = ridx[c] - r0;
-          if (r >= 0 && r < rows) acc[r * d.D + k] = fmaf(g[c], __ldg(p.word + (size_t)c * d.D + k), acc[r * d.D + k]);
-        }
-      }
-      __syncthreads();
-      float* dst = p.gvis + ((size_t)f * d.Nb + r0) * d.D;
-      if (f == 0 && p.train) {
-        float* cl = w.clus + (size_t)r0 * d.D;
-        for (int i = tid; i < rows * d.D; i += kBwdThreads) {
-          dst[i] = acc[i] + cl[i];
-          cl[i] = 0.f;  // leave the accumulators clean for the next step
-        }
-      } else {
-        for (int i = tid; i < rows * d.D; i += kBwdThreads) dst[i] = acc[i];
-      }
-      __syncthreads();
-    }
-  } else {
-    const int c = blockIdx.x - d.F;
-    float* dst = p.gword + (size_t)c * d.D;
-    const bool live = (c % d.Ne) < __ldg(p.lens + c / d.Ne);
-    if (!live) {
-      for (int k = tid; k < d.D; k += kBwdThreads) dst[k] = 0.f;
-      return;
-    }
-    float* g = sm;                                  // [F]
-    int* ridx = reinterpret_cast<int*>(sm + d.F);   // [F]
-    for (int a = tid; a < d.Na; a += kBwdThreads) {
-      float tmp[kMaxNsLocal];
-      col_grad(p, w, a, c, gout, tmp);
-      for (int s = 0; s < d.Ns; ++s) {
-        g[a * d.Ns + s] = tmp[s];
-        ridx[a * d.Ns + s] = (a * d.Ns + s) * d.Nb + (int)__ldg(p.D_ind + (size_t)(a * d.Ns + s) * d.NQ + c);
-      }
-    }
-    __syncthreads();
-    for (int k = tid; k < d.D; k += kBwdThreads) {
-      float accv = 0.f;
-      for (int f = 0; f < d.F; ++f) accv = fmaf(g[f], __ldg(p.vis + (size_t)ridx[f] * d.D + k), accv);
-      dst[k] = accv;
     }
   }
 }
@@ -674,8 +787,10 @@ NAFAE_API int nafae_ground_forward(const float* vis_feats, const float* word_fea
   // shared memory: row tile (+ parked partial sums when D > 512), reused by P2's small tables
   size_t smem = (size_t)kRowTile * d.D * 4;
   if (d.D > 32 * kKS) smem += (size_t)kFwdWarps * 4 * kRowTile * 4;
-  const size_t p2 = (size_t)48 * d.Ns * 4;
-  if (train && p2 > smem) smem = p2;
+  const size_t p2 = ((size_t)2 * d.Ns * d.NQ + 2 * (size_t)d.NQ + (size_t)d.Ne * d.Ns) * 4;
+  const size_t p3 = (size_t)2 * d.Na * d.Ns * d.Na * 4;
+  if (p2 > smem) smem = p2;
+  if (p3 > smem) smem = p3;
   NAFAE_REQUIRE(smem <= 200 * 1024, "ground: D=%d / Ns=%d need too much shared memory", d.D, d.Ns);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(ground_fwd_kernel,
@@ -715,14 +830,9 @@ NAFAE_API int nafae_ground_backward(const float* grad_margin_loss, const float* 
   p.d = d;
   p.vis_lam = vis_lam;
   p.train = train ? 1 : 0;
-  if (p.train) {
-    const size_t smem = ((size_t)d.D + 4 * d.Ns) * 4;
-    ground_bwd_cluster_kernel<<<d.NQ, kBwdThreads, smem, stream>>>(p);
-    const int st = launch_status("ground_bwd_cluster_kernel");
-    if (st != 1) return st;
-  }
-  size_t smem = ((size_t)2 * d.NQ + (size_t)kRowTile * d.D) * 4;
-  const size_t smem_w = (size_t)2 * d.F * 4;
+  size_t smem = ((size_t)2 * d.Ns * d.NQ + (size_t)d.Ns * d.Na + 2 * (size_t)d.NQ +
+                 (size_t)kRowTile * d.D + 4) * 4;
+  const size_t smem_w = (size_t)4 * d.F * 4;
   if (smem_w > smem) smem = smem_w;
   NAFAE_REQUIRE(smem <= 200 * 1024, "ground backward: sizes need too much shared memory");
   if (smem > 48 * 1024) {
@@ -734,7 +844,11 @@ NAFAE_API int nafae_ground_backward(const float* grad_margin_loss, const float* 
     }
   }
   ground_bwd_main_kernel<<<d.F + d.NQ, kBwdThreads, smem, stream>>>(p);
-  return launch_status("ground_bwd_main_kernel");
+  int st = launch_status("ground_bwd_main_kernel");
+  if (st != 1 || !p.train) return st;
+  const size_t smem_c = ((size_t)d.D + 4 * d.Ns) * 4;
+  ground_bwd_cluster_kernel<<<d.NQ, kBwdThreads, smem_c, stream>>>(p);
+  return launch_status("ground_bwd_cluster_kernel");
 }
 
 NAFAE_API int nafae_ground_postprocess(const int64_t* D_ind, const float* D_sim, int Na, int Ns,

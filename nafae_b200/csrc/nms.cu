@@ -206,24 +206,29 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int n, int col_blo
 
 // ------------------------------------------------------- fused proposal-layer tail ----
 
-// grid F, block 64, dynamic smem = post_topn * sizeof(RowBox).
+// grid F, block 256 (4 threads per candidate), dynamic smem = post_topn * sizeof(RowBox).
 // One chunk = 64 consecutive candidates (score order).  Per chunk:
-//   1. every thread tests its candidate against the kept list (a = kept box, b = candidate)
-//   2. survivors compute their row of the chunk's diagonal tile (a = this box, b = later box)
-//   3. thread 0 resolves the chunk greedily (64-step bit scan), stopping at post_topn
+//   1. every candidate is tested against the kept list (a = kept box, b = candidate); the four
+//      threads of a candidate split the list and OR their verdicts
+//   2. survivors compute their row of the chunk's diagonal tile (a = this box, b = later box),
+//      again split four ways
+//   3. lane 0 resolves the chunk greedily (64-step bit scan), stopping at post_topn
 //   4. the newly kept boxes are appended to the kept list and written out
-__global__ void __launch_bounds__(kTile)
+constexpr int kTailThreads = 4 * kTile;
+
+__global__ void __launch_bounds__(kTailThreads)
 proposal_tail_kernel(const float* __restrict__ proposals, const float* __restrict__ scores, int n,
                      int m, int post_topn, Thresh th, float* __restrict__ rois,
                      float* __restrict__ roi_scores, int* __restrict__ num_kept) {
   extern __shared__ RowBox kept[];  // post_topn entries
   __shared__ ColBox chunk[kTile];
   __shared__ unsigned long long diag[kTile];
-  __shared__ unsigned s_sup[2];
+  __shared__ int s_flag[kTile];
   __shared__ unsigned long long s_new;
   __shared__ int s_count;
 
   const int f = blockIdx.x, tid = threadIdx.x;
+  const int t = tid >> 2, q = tid & 3;  // candidate slot, quarter
   const float* fp = proposals + (size_t)f * n * 4;
   const float* fs = scores + (size_t)f * n;
   float* out = rois + (size_t)f * post_topn * 5;
@@ -235,42 +240,60 @@ proposal_tail_kernel(const float* __restrict__ proposals, const float* __restric
     const int count = s_count;
     if (count >= post_topn) break;  // uniform: early exit, the rest of the frame is never read
     const int size = min(m - c0, kTile);
-    const bool valid = tid < size;
+    const bool valid = t < size;
     float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) bx = *reinterpret_cast<const float4*>(fp + (size_t)(c0 + tid) * 4);
+    if (valid) bx = __ldg(reinterpret_cast<const float4*>(fp + (size_t)(c0 + t) * 4));
     const ColBox cb = make_col(bx.x, bx.y, bx.z, bx.w);
-    chunk[tid] = cb;
-    bool sup = !valid;
-    for (int k = 0; k < count && !sup; ++k) sup = iou_exceeds(kept[k], cb, th);
-    const unsigned bal = __ballot_sync(0xffffffffu, sup);
-    if ((tid & 31) == 0) s_sup[tid >> 5] = bal;
+    if (q == 0) chunk[t] = cb;
+    int sup = valid ? 0 : 1;
+    if (valid) {
+#pragma unroll 2
+      for (int k = q; k < count; k += 4) sup |= iou_exceeds(kept[k], cb, th) ? 1 : 0;
+    }
+    sup |= __shfl_xor_sync(0xffffffffu, sup, 1);
+    sup |= __shfl_xor_sync(0xffffffffu, sup, 2);
+    if (q == 0) s_flag[t] = sup;
     __syncthreads();
-    unsigned long long d = 0;
+    unsigned dlo = 0, dhi = 0;
     if (!sup) {
       const RowBox a = make_row(bx.x, bx.y, bx.z, bx.w);
-      for (int j = tid + 1; j < size; ++j)
-        if (iou_exceeds(a, chunk[j], th)) d |= 1ULL << j;
-    }
-    diag[tid] = d;
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long w = ((unsigned long long)s_sup[1] << 32) | s_sup[0];
-      unsigned long long kb = 0;
-      int cnt = count;
-      for (int k = 0; k < size && cnt < post_topn; ++k) {
-        if (!((w >> k) & 1ULL)) {
-          kb |= 1ULL << k;
-          w |= diag[k];
-          ++cnt;
+#pragma unroll 2
+      for (int j = t + 1 + q; j < size; j += 4)
+        if (iou_exceeds(a, chunk[j], th)) {
+          if (j < 32) dlo |= 1u << j;
+          else dhi |= 1u << (j - 32);
         }
+    }
+    dlo |= __shfl_xor_sync(0xffffffffu, dlo, 1);
+    dhi |= __shfl_xor_sync(0xffffffffu, dhi, 1);
+    dlo |= __shfl_xor_sync(0xffffffffu, dlo, 2);
+    dhi |= __shfl_xor_sync(0xffffffffu, dhi, 2);
+    if (q == 0) diag[t] = ((unsigned long long)dhi << 32) | dlo;
+    __syncthreads();
+    if (tid < 32) {
+      const unsigned lo = __ballot_sync(0xffffffffu, s_flag[tid] != 0);
+      const unsigned hi = __ballot_sync(0xffffffffu, s_flag[tid + 32] != 0);
+      if (tid == 0) {
+        unsigned long long w = ((unsigned long long)hi << 32) | lo;
+        unsigned long long kb = 0;
+        int cnt = count;
+#pragma unroll 8
+        for (int k = 0; k < kTile; ++k) {
+          const unsigned long long dk = diag[k];
+          if (!((w >> k) & 1ULL) && cnt < post_topn) {
+            kb |= 1ULL << k;
+            w |= dk;
+            ++cnt;
+          }
+        }
+        s_new = kb;
+        s_count = cnt;
       }
-      s_new = kb;
-      s_count = cnt;
     }
     __syncthreads();
     const unsigned long long kb = s_new;
-    if ((kb >> tid) & 1ULL) {
-      const int pos = count + __popcll(kb & ((1ULL << tid) - 1ULL));
+    if (q == 0 && ((kb >> t) & 1ULL)) {
+      const int pos = count + __popcll(kb & ((1ULL << t) - 1ULL));
       kept[pos] = make_row(bx.x, bx.y, bx.z, bx.w);
       float* o = out + (size_t)pos * 5;
       o[0] = (float)f;
@@ -278,13 +301,13 @@ proposal_tail_kernel(const float* __restrict__ proposals, const float* __restric
       o[2] = bx.y;
       o[3] = bx.z;
       o[4] = bx.w;
-      out_s[pos] = fs[c0 + tid];
+      out_s[pos] = fs[c0 + t];
     }
     __syncthreads();
   }
   // zero padding, frame index in column 0 of every row (proposal_layer.py:127,160)
   const int count = s_count;
-  for (int k = count + tid; k < post_topn; k += kTile) {
+  for (int k = count + tid; k < post_topn; k += kTailThreads) {
     float* o = out + (size_t)k * 5;
     o[0] = (float)f;
     o[1] = o[2] = o[3] = o[4] = 0.f;
@@ -394,7 +417,7 @@ NAFAE_API int nafae_proposal_tail(const float* proposals, const float* scores, i
     }
   }
   const Thresh th = make_thresh(nms_thresh);
-  proposal_tail_kernel<<<num_frames, kTile, smem, stream>>>(proposals, scores, boxes_num, m,
+  proposal_tail_kernel<<<num_frames, kTailThreads, smem, stream>>>(proposals, scores, boxes_num, m,
                                                             post_nms_topn, th, rois, roi_scores,
                                                             num_kept);
   return launch_status("proposal_tail_kernel");

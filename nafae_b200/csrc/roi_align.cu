@@ -227,18 +227,32 @@ align_bwd_generic(const float* __restrict__ top_diff, const float* __restrict__ 
 // --------------------------------------------------------------- bandwidth kernel ----
 // 7x7 output from an 8x8 sample grid (RoIAlignAvg/Max(7, 7, s): the only configuration the
 // reference instantiates, faster_rcnn/rpn.py:34).
+//
+// Persistent CTAs (one per SM).  Work unit = (frame, group of cg channels): its NCHW slab is
+// contiguous in HBM and is staged into shared memory by 1-D bulk async copies (TMA engine) through
+// a ring of `stages` buffers with full/empty mbarriers: a dedicated producer warp keeps the ring
+// full, 16 consumer warps drain it and never meet at a CTA-wide barrier except when the frame
+// (and with it the RoI table) changes.  Pass-groups (RoI x 4*CPL channels) are dealt round-robin
+// to the consumer warps across unit boundaries, so a 20-RoI frame keeps 16 warps evenly busy.
+// Inside a pass a lane owns one sample column (pw) of CPL channels: the RoI's row offsets and
+// weights are warp-uniform table reads, the taps are LDS with compile-time offsets (W and the
+// padded channel stride are template constants for the two production map sizes), the 2x2 pool is
+// one shuffle per sample row.  For POOL_AVG the 1/4 is folded into the column weights.
 constexpr int kOut = 7;
-constexpr int kS = 8;             // sample grid side
-constexpr int kSlabThreads = 512;
-constexpr int kSlabWarps = kSlabThreads / 32;
-constexpr int kMaxRoiTable = 128;  // RoIs of one frame resident in the table at a time
+constexpr int kS = 8;               // sample grid side
+constexpr int kConsWarps = 16;
+constexpr int kConsThreads = kConsWarps * 32;
+constexpr int kSlabThreads = kConsThreads + 32;  // + producer warp
+constexpr int kMaxRoiTable = 128;   // RoIs of one frame resident in the table at a time
 constexpr int kStagesMax = 4;
 
-struct __align__(16) RoiEntry {  // 128 B: everything a pass needs about one RoI
-  int hoff[kS];              // hstart * W, or -1 if that sample row is outside
-  float hr[kS];
-  int woff[kS];              // wstart, or -1 if that sample column is outside
-  float wr[kS];
+struct __align__(16) RoiEntry {  // 192 B: everything a pass needs about one RoI
+  int hoff_b[kS];   // byte offset of row hstart (hstart*W*4); 0 if the sample row is outside
+  float h0[kS];     // 1-h_ratio, 0 if outside
+  float h1[kS];     // h_ratio,   0 if outside
+  int woff_b[kS];   // byte offset of column wstart; 0 if the sample column is outside
+  float w0[kS];     // (1-w_ratio) [* 1/4 for avg], 0 if outside
+  float w1[kS];     // w_ratio     [* 1/4 for avg], 0 if outside
 };
 
 struct SlabParams {
@@ -247,7 +261,7 @@ struct SlabParams {
   float* top;
   float scale;
   int B, R, H, W, C;
-  int cg;          // channels per slab (multiple of 4)
+  int cg;          // channels per slab
   int groups;      // C / cg
   int hw;          // H*W
   int hwp;         // padded per-channel stride in shared memory (floats), hwp % 32 == 8
@@ -255,16 +269,26 @@ struct SlabParams {
   int units;       // B * groups
 };
 
-template <int POOL>
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cons_barrier() {  // the 16 consumer warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory");
+}
+
+template <int POOL, int W_CT, int HWP_CT, int CPL>
 __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const SlabParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: [stages][cg][hwp] floats | RoiEntry[kMaxRoiTable] | int roi_id[kMaxRoiTable] | bars
   float* slabs = reinterpret_cast<float*>(smem_raw);
-  const size_t stage_floats = (size_t)p.cg * p.hwp;
+  const int W = W_CT ? W_CT : p.W;
+  const int hwp = HWP_CT ? HWP_CT : p.hwp;
+  const size_t stage_floats = (size_t)p.cg * hwp;
   RoiEntry* table = reinterpret_cast<RoiEntry*>(slabs + stage_floats * p.stages);
   int* roi_id = reinterpret_cast<int*>(table + kMaxRoiTable);
   uint64_t* full = reinterpret_cast<uint64_t*>(roi_id + kMaxRoiTable);
-  __shared__ int s_nroi, s_next, s_warp_cnt[kSlabWarps];
+  uint64_t* empty = full + kStagesMax;
+  __shared__ int s_nroi, s_next, s_warp_cnt[kConsWarps];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // contiguous unit range per CTA so that the RoI table is rebuilt at most ~twice
@@ -272,26 +296,36 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
   const int u_end = (int)((long long)p.units * (blockIdx.x + 1) / gridDim.x);
 
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kConsWarps);
+    }
     fence_mbar_init();
   }
   __syncthreads();
 
-  const uint32_t chan_bytes = (uint32_t)p.hw * 4u;
-  auto issue = [&](int u, int stage) {  // thread 0 only
-    const int f = u / p.groups, gidx = u % p.groups;
-    const float* src = p.bottom + ((size_t)f * p.C + (size_t)gidx * p.cg) * p.hw;
-    float* dst = slabs + stage_floats * stage;
-    mbar_arrive_expect_tx(&full[stage], chan_bytes * p.cg);
-    for (int c = 0; c < p.cg; ++c)
-      bulk_g2s(dst + (size_t)c * p.hwp, src + (size_t)c * p.hw, chan_bytes, &full[stage]);
-  };
-  if (tid == 0)
-    for (int s = 0; s < p.stages && u_begin + s < u_end; ++s) issue(u_begin + s, s);
+  if (warp == kConsWarps) {
+    // ------------------------------------------------------------ producer warp ----
+    if (lane == 0) {
+      const uint32_t chan_bytes = (uint32_t)p.hw * 4u;
+      for (int u = u_begin; u < u_end; ++u) {
+        const int it = u - u_begin, stage = it % p.stages;
+        if (it >= p.stages) mbar_wait(&empty[stage], (uint32_t)(it / p.stages - 1) & 1u);
+        const int f = u / p.groups, gidx = u % p.groups;
+        const float* src = p.bottom + ((size_t)f * p.C + (size_t)gidx * p.cg) * p.hw;
+        float* dst = slabs + stage_floats * stage;
+        mbar_arrive_expect_tx(&full[stage], chan_bytes * p.cg);
+        for (int c = 0; c < p.cg; ++c)
+          bulk_g2s(dst + (size_t)c * hwp, src + (size_t)c * p.hw, chan_bytes, &full[stage]);
+      }
+    }
+    return;
+  }
 
+  // -------------------------------------------------------------- consumer warps ----
   // RoIs whose batch index is outside [0, B): defined as all-zero rows (CTA 0 writes them)
   if (blockIdx.x == 0) {
-    for (int r = warp; r < p.R; r += kSlabWarps) {
+    for (int r = warp; r < p.R; r += kConsWarps) {
       const int b = (int)p.rois[(size_t)r * 5];
       if (b < 0 || b >= p.B) {
         float* o = p.top + (size_t)r * p.C * (kOut * kOut);
@@ -302,23 +336,23 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
 
   // Fill the RoI table with the next (at most kMaxRoiTable) RoIs of frame f whose index is
   // >= r_start, in ascending index order; s_next = index where the following chunk starts
-  // (>= R when the frame is exhausted).
+  // (>= R when the frame is exhausted).  Called by all consumer warps together.
   auto build_table = [&](int f, int r_start) {
-    __syncthreads();  // every warp is done with the previous table contents
+    cons_barrier();  // every warp is done with the previous table contents
     if (tid == 0) {
       s_nroi = 0;
       s_next = p.R;
     }
-    __syncthreads();
-    for (int base = r_start; base < p.R; base += kSlabThreads) {
+    cons_barrier();
+    for (int base = r_start; base < p.R; base += kConsThreads) {
       const int r = base + tid;
       const bool hit = r < p.R && (int)p.rois[(size_t)r * 5] == f;
       const unsigned bal = __ballot_sync(0xffffffffu, hit);
       if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-      __syncthreads();
+      cons_barrier();
       const int have = s_nroi;
       int before = have, tot = 0;
-      for (int w = 0; w < kSlabWarps; ++w) {
+      for (int w = 0; w < kConsWarps; ++w) {
         const int cw = s_warp_cnt[w];
         if (w < warp) before += cw;
         tot += cw;
@@ -326,46 +360,50 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
       const int pos = before + __popc(bal & ((1u << lane) - 1u));
       if (hit && pos < kMaxRoiTable) roi_id[pos] = r;
       if (hit && pos == kMaxRoiTable) s_next = r;  // first RoI that did not fit (unique thread)
-      __syncthreads();
+      cons_barrier();
       if (have + tot >= kMaxRoiTable) {  // uniform
         if (tid == 0) {
           s_nroi = kMaxRoiTable;
-          if (have + tot == kMaxRoiTable) s_next = min(base + kSlabThreads, p.R);
+          if (have + tot == kMaxRoiTable) s_next = min(base + kConsThreads, p.R);
         }
         break;
       }
       if (tid == 0) s_nroi = have + tot;
     }
-    __syncthreads();
+    cons_barrier();
     const int nroi = s_nroi;
+    const float wscale = POOL == NAFAE_POOL_AVG ? 0.25f : 1.f;
     // geometry: one thread per (RoI, axis, sample index)
-    for (int e = tid; e < nroi * 2 * kS; e += kSlabThreads) {
+    for (int e = tid; e < nroi * 2 * kS; e += kConsThreads) {
       const int j = e / (2 * kS), k = e % (2 * kS);
       const RoiGeom g = roi_geom(p.rois + (size_t)roi_id[j] * 5, p.scale, kS, kS);
       int cell;
       float ratio;
       if (k < kS) {
         const bool ok = axis_sample(g.start_h, g.bin_h, k, p.H, &cell, &ratio);
-        table[j].hoff[k] = ok ? cell * p.W : -1;
-        table[j].hr[k] = ratio;
+        table[j].hoff_b[k] = ok ? cell * W * 4 : 0;
+        table[j].h0[k] = ok ? 1.f - ratio : 0.f;
+        table[j].h1[k] = ok ? ratio : 0.f;
       } else {
         const bool ok = axis_sample(g.start_w, g.bin_w, k - kS, p.W, &cell, &ratio);
-        table[j].woff[k - kS] = ok ? cell : -1;
-        table[j].wr[k - kS] = ratio;
+        table[j].woff_b[k - kS] = ok ? cell * 4 : 0;
+        table[j].w0[k - kS] = ok ? wscale * (1.f - ratio) : 0.f;
+        table[j].w1[k - kS] = ok ? wscale * ratio : 0.f;
       }
     }
-    __syncthreads();
+    cons_barrier();
   };
 
   int cur_f = -1, cur_start = -1;  // which (frame, chunk start) the table holds
-  const int quads = p.cg >> 2;
+  const int nblk = p.cg / (4 * CPL);  // channel blocks per RoI inside a unit
   const int cq = lane >> 3, pw = lane & 7;
+  int g_base = 0;  // running pass-group counter (uniform): deals groups round-robin to warps
   for (int u = u_begin; u < u_end; ++u) {
     const int it = u - u_begin;
     const int stage = it % p.stages;
     const uint32_t parity = (uint32_t)(it / p.stages) & 1u;
     const int f = u / p.groups, gidx = u % p.groups;
-    const float* slab = slabs + stage_floats * stage;
+    const unsigned char* slab = reinterpret_cast<const unsigned char*>(slabs + stage_floats * stage);
     bool waited = false;
     int r_next = 0;
     do {
@@ -380,37 +418,67 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
         mbar_wait(&full[stage], parity);
         waited = true;
       }
-      // one pass = (RoI j, 4 consecutive channels); lane = (channel cq, sample column pw)
-      for (int pass = warp; pass < nroi * quads; pass += kSlabWarps) {
-        const int j = pass / quads, q = pass % quads;
+      const int ng = nroi * nblk;
+      for (int idx = (warp - g_base) & (kConsWarps - 1); idx < ng; idx += kConsWarps) {
+        const int j = idx / nblk, blk = idx - j * nblk;
         const RoiEntry& e = table[j];
-        const int wo = e.woff[pw];
-        const float wr = e.wr[pw];
-        const float* base = slab + (size_t)(q * 4 + cq) * p.hwp + (wo < 0 ? 0 : wo);
-        float s[kS];
+        const float w0 = e.w0[pw], w1 = e.w1[pw];
+        const int ch0 = blk * (4 * CPL) + cq;  // first channel of this lane inside the slab
+        const unsigned char* lane_base = slab + (size_t)ch0 * hwp * 4 + e.woff_b[pw];
+        int hoff[kS];
+        float h0[kS], h1[kS];
+#pragma unroll
+        for (int v = 0; v < kS; v += 4) {
+          const int4 o4 = *reinterpret_cast<const int4*>(&e.hoff_b[v]);
+          const float4 a4 = *reinterpret_cast<const float4*>(&e.h0[v]);
+          const float4 b4 = *reinterpret_cast<const float4*>(&e.h1[v]);
+          hoff[v] = o4.x; hoff[v + 1] = o4.y; hoff[v + 2] = o4.z; hoff[v + 3] = o4.w;
+          h0[v] = a4.x; h0[v + 1] = a4.y; h0[v + 2] = a4.z; h0[v + 3] = a4.w;
+          h1[v] = b4.x; h1[v + 1] = b4.y; h1[v + 2] = b4.z; h1[v + 3] = b4.w;
+        }
+        float s[CPL][kS];
 #pragma unroll
         for (int ph = 0; ph < kS; ++ph) {
-          const int ho = e.hoff[ph];
-          const float* t = base + (ho < 0 ? 0 : ho);
-          const float v = interp_fast(t[0], t[1], t[p.W], t[p.W + 1], e.hr[ph], wr);
-          s[ph] = (ho < 0 || wo < 0) ? 0.f : v;
-        }
-        const int c = gidx * p.cg + q * 4 + cq;
-        float* o = p.top + ((size_t)roi_id[j] * p.C + c) * (kOut * kOut) + pw;
-        float right_prev = __shfl_down_sync(0xffffffffu, s[0], 1);
+          const unsigned char* t = lane_base + hoff[ph];
 #pragma unroll
-        for (int i = 0; i < kOut; ++i) {
-          const float right_next = __shfl_down_sync(0xffffffffu, s[i + 1], 1);
-          const float v = pool4(POOL, s[i], right_prev, s[i + 1], right_next);
-          if (pw < kOut) o[i * kOut] = v;
-          right_prev = right_next;
+          for (int k = 0; k < CPL; ++k) {
+            const float* q = reinterpret_cast<const float*>(t + (size_t)k * 4 * hwp * 4);
+            const float top = fmaf(q[1], w1, q[0] * w0);
+            const float bot = fmaf(q[W + 1], w1, q[W] * w0);
+            s[k][ph] = fmaf(bot, h1[ph], top * h0[ph]);
+          }
+        }
+        const int c_first = gidx * p.cg + ch0;
+        float* o = p.top + ((size_t)roi_id[j] * p.C + c_first) * (kOut * kOut) + pw;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          float* ok = o + (size_t)k * 4 * (kOut * kOut);
+          if (POOL == NAFAE_POOL_AVG) {
+            float hs_prev = s[k][0] + __shfl_down_sync(0xffffffffu, s[k][0], 1);
+#pragma unroll
+            for (int i = 0; i < kOut; ++i) {
+              const float hs = s[k][i + 1] + __shfl_down_sync(0xffffffffu, s[k][i + 1], 1);
+              if (pw < kOut) ok[i * kOut] = hs_prev + hs;
+              hs_prev = hs;
+            }
+          } else {
+            float right_prev = __shfl_down_sync(0xffffffffu, s[k][0], 1);
+#pragma unroll
+            for (int i = 0; i < kOut; ++i) {
+              const float right_next = __shfl_down_sync(0xffffffffu, s[k][i + 1], 1);
+              const float v = pool4(POOL, s[k][i], right_prev, s[k][i + 1], right_next);
+              if (pw < kOut) ok[i * kOut] = v;
+              right_prev = right_next;
+            }
+          }
         }
       }
+      g_base += ng;
       r_next = next_after;
     } while (r_next < p.R);
 
-    __syncthreads();  // every warp is done with this stage
-    if (tid == 0 && u + p.stages < u_end) issue(u + p.stages, stage);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);  // this warp is done with the stage
   }
 }
 
@@ -426,25 +494,40 @@ int smem_optin_limit() {
   return cached;
 }
 
+template <int W_CT, int HWP_CT, int CPL>
+int launch_slab(const SlabParams& p, int pool, size_t smem, cudaStream_t stream) {
+  auto kern = pool == NAFAE_POOL_AVG ? align_pool_fwd_slab<NAFAE_POOL_AVG, W_CT, HWP_CT, CPL>
+                                     : align_pool_fwd_slab<NAFAE_POOL_MAX, W_CT, HWP_CT, CPL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("roi_align: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    return -(int)e;
+  }
+  int grid = sm_count();
+  if (grid > p.units) grid = p.units;
+  kern<<<grid, kSlabThreads, smem, stream>>>(p);
+  return launch_status("align_pool_fwd_slab");
+}
+
 // Returns 1 if the slab kernel was launched, 0 if the shape is not eligible (caller falls back),
 // <0 on a launch error.
 int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W, int C, int pool,
                     const float* rois, float* top, cudaStream_t stream) {
   const int hw = H * W;
-  if (hw % 4 != 0 || C % 4 != 0 || H < 2 || W < 2) return 0;
+  if (hw % 4 != 0 || C % 8 != 0 || H < 2 || W < 2) return 0;
   if ((reinterpret_cast<uintptr_t>(bottom) & 15) != 0) return 0;
   if ((long long)R * 5 >= (1ll << 31)) return 0;
   int hwp = hw;
   while (hwp % 32 != 8) hwp += 4;
   const size_t fixed = sizeof(RoiEntry) * kMaxRoiTable + sizeof(int) * kMaxRoiTable +
-                       sizeof(uint64_t) * kStagesMax + 128;
+                       sizeof(uint64_t) * 2 * kStagesMax + 128;
   const size_t budget = (size_t)smem_optin_limit() - 1024;  // static smem + slack
   int cg = 0, stages = 0;
   // prefer >= 3 stages with a slab of <= 64 KB
-  for (int cand : {32, 16, 8, 4}) {
+  for (int cand : {32, 16, 8}) {
     if (C % cand) continue;
     const size_t stage_bytes = (size_t)cand * hwp * 4;
-    if (stage_bytes > 64 * 1024 && cand > 4) continue;
+    if (stage_bytes > 64 * 1024 && cand > 8) continue;
     int st = (int)((budget - fixed) / stage_bytes);
     if (st > kStagesMax) st = kStagesMax;
     if (st >= 2) {
@@ -472,17 +555,9 @@ int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W
   p.stages = stages;
   p.units = B * p.groups;
   const size_t smem = (size_t)cg * hwp * 4 * stages + fixed;
-  auto kern = pool == NAFAE_POOL_AVG ? align_pool_fwd_slab<NAFAE_POOL_AVG>
-                                     : align_pool_fwd_slab<NAFAE_POOL_MAX>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    set_error("roi_align: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-    return -(int)e;
-  }
-  int grid = sm_count();
-  if (grid > p.units) grid = p.units;
-  kern<<<grid, kSlabThreads, smem, stream>>>(p);
-  return launch_status("align_pool_fwd_slab");
+  if (W == 50 && hwp == 1928) return launch_slab<50, 1928, 2>(p, pool, smem, stream);  // 38x50 maps
+  if (W == 14 && hwp == 200 && cg == 32) return launch_slab<14, 200, 4>(p, pool, smem, stream);  // 14x14
+  return launch_slab<0, 0, 2>(p, pool, smem, stream);
 }
 
 int grid_for(long long total) {
