@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnafae_b200.so")
+LIB_PATH = os.environ.get("NAFAE_B200_LIB", os.path.join(_HERE, "libnafae_b200.so"))  # override: debug builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

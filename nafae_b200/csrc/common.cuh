@@ -85,6 +85,15 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// "Last CTA to arrive continues" ticket: ONE thread publishes the whole CTA's prior global writes
+// (callers do __syncthreads() first; release is cumulative over the barrier) and acquires the
+// other CTAs' -- much cheaper than every thread executing __threadfence() (fence.sc.gpu).
+__device__ __forceinline__ int ticket_acq_rel(int* counter) {
+  int old;
+  asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+  return old;
+}
+
 template <int N>
 __device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");

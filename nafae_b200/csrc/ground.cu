@@ -26,9 +26,22 @@ namespace nafae {
 namespace {
 
 constexpr float kEps = 1e-5f;  // model.py:33
+
+#ifdef NAFAE_TRACE
+__device__ unsigned long long g_trace[256];
+__device__ __forceinline__ void trace(int slot) {
+  // SM-local cycle counter: cheap (globaltimer reads cost ~0.5 us each and distort the trace);
+  // only differences taken on the same CTA are meaningful
+  g_trace[slot] = (unsigned long long)clock64();
+}
+#define TRACE(slot) do { if (threadIdx.x == 0) trace(slot); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
 constexpr int kFwdThreads = 256;
 constexpr int kFwdWarps = kFwdThreads / 32;
-constexpr int kColsPerCta = 32;  // 8 warps x 4 columns
+constexpr int kColsPerCta = 8;   // live columns per CTA: 2 column groups x 4 row groups of warps
+constexpr int kLiveMax = 2048;   // Na * Ne upper bound for the compacted column list
 constexpr int kRowTile = 32;     // boxes staged in shared memory at a time
 constexpr int kKS = 16;          // k-slices per lane per chunk: 512 features per chunk
 
@@ -87,16 +100,16 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Warp-cooperative dot product of two global rows with the loads issued in independent batches
 // of 8 per lane (a plain k-loop with a runtime trip count serialises on L2 latency).
-__device__ __forceinline__ float warp_dot(const float* __restrict__ x, const float* __restrict__ y,
-                                          int D, int lane) {
+// x / y may point to global OR shared memory (generic loads).
+__device__ __forceinline__ float warp_dot(const float* x, const float* y, int D, int lane) {
   float acc = 0.f;
   for (int k0 = 0; k0 < D; k0 += 256) {
     float a[8], b[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = k0 + lane + 32 * j;
-      a[j] = k < D ? __ldg(x + k) : 0.f;
-      b[j] = k < D ? __ldg(y + k) : 0.f;
+      a[j] = k < D ? x[k] : 0.f;
+      b[j] = k < D ? y[k] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc = fmaf(a[j], b[j], acc);
@@ -125,144 +138,228 @@ struct FwdParams {
   int col_chunks;
 };
 
-// 4 per-lane partial sums -> lane group (lane>>3) holds the total of column (lane>>3)
-__device__ __forceinline__ float reduce4(float a0, float a1, float a2, float a3, int lane) {
-  // xor 16: lanes 0-15 keep columns 0,1; lanes 16-31 keep columns 2,3
-  const bool hi = lane & 16;
-  float k0 = hi ? a2 : a0, k1 = hi ? a3 : a1;
-  float s0 = hi ? a0 : a2, s1 = hi ? a1 : a3;
-  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-  // xor 8: within each half, lanes with bit3 clear keep the first column
-  const bool hi2 = lane & 8;
-  float k = hi2 ? k1 : k0, s = hi2 ? k0 : k1;
-  k += __shfl_xor_sync(0xffffffffu, s, 8);
-  k += __shfl_xor_sync(0xffffffffu, k, 4);
-  k += __shfl_xor_sync(0xffffffffu, k, 2);
-  k += __shfl_xor_sync(0xffffffffu, k, 1);
-  return k;  // column index = (lane >> 3): 0,1 for lanes 0-15 ; 2,3 for lanes 16-31
+// 16 per-lane partial sums -> lanes 2*i and 2*i+1 both hold the warp total of value i.
+// 16 shuffles, dependency depth 5 (a per-value butterfly would be 80 shuffles, depth 5 each).
+__device__ __forceinline__ float reduce16(const float (&v)[16], int lane) {
+  float k8[8], k4[4], k2[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = h16 ? v[8 + i] : v[i], send = h16 ? v[i] : v[8 + i];
+    k8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h8 ? k8[4 + i] : k8[i], send = h8 ? k8[i] : k8[4 + i];
+    k4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = h4 ? k4[2 + i] : k4[i], send = h4 ? k4[i] : k4[2 + i];
+    k2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float keep = h2 ? k2[1] : k2[0], send = h2 ? k2[0] : k2[1];
+  float k1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+  return k1;  // value index = lane >> 1
 }
 
-__device__ void phase2_segment(const FwdParams& p, const Ws& w, int a, float* sm);
-__device__ void phase3_final(const FwdParams& p, const Ws& w, float* sm);
+__device__ void phase2_segment(const FwdParams& p, const Ws& w, int a);
+__device__ void phase3_final(const FwdParams& p, const Ws& w);
 
-__global__ void __launch_bounds__(kFwdThreads) ground_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) ground_fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(16) float sm[];  // kRowTile * D floats (vis rows of the frame)
   __shared__ int s_ticket;
+  __shared__ int s_live[kLiveMax];       // compacted list of live (unmasked) columns
+  __shared__ int s_nlive;
+  __shared__ float s_best[kColsPerCta][16];
+  __shared__ int s_besti[kColsPerCta][16];
+  __shared__ __align__(8) uint64_t s_bar;
   const Dims& d = p.d;
   const Ws w = ws_carve(p.ws, d);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int f = blockIdx.x / p.col_chunks, chunk = blockIdx.x % p.col_chunks;
   const int a = f / d.Ns;
+  if (blockIdx.x == 0) TRACE(0);
 
-  // ---- P1: one frame x up to 32 columns; each warp owns 4 consecutive columns
-  const int c_base = chunk * kColsPerCta + warp * 4;
-  bool live[4];
-  bool any_live = false;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c_base + j;
-    live[j] = c < d.NQ && (c % d.Ne) < __ldg(p.lens + c / d.Ne);  // model.py:535-536
-    any_live |= live[j];
-  }
-  const int my_col = c_base + (lane >> 3);  // column this lane reports after reduce4
-  float best = -INFINITY;
-  int best_r = 0;
+  // ---- P1: one frame x 8 LIVE columns per CTA pass.  Masked columns (e >= len[a'],
+  // model.py:535-536) are never computed: the column list is compacted first.
+  // warp = (column group of 4: warp & 1) x (row group: warp >> 1).
   const float* vis_f = p.vis + (size_t)f * d.Nb * d.D;
-
-  __shared__ __align__(8) uint64_t s_bar;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     fence_mbar_init();
+    // first row tile: one bulk async copy (TMA engine), in flight while the columns are compacted
+    const uint32_t bytes = (uint32_t)min(kRowTile, d.Nb) * d.D * 4u;
+    mbar_arrive_expect_tx(&s_bar, bytes);
+    bulk_g2s(sm, vis_f, bytes, &s_bar);
   }
-  uint32_t parity = 0;
-  for (int r0 = 0; r0 < d.Nb; r0 += kRowTile) {
-    const int rows = min(kRowTile, d.Nb - r0);
-    __syncthreads();  // previous tile consumed (and the barrier init is visible)
-    if (tid == 0) {   // one bulk async copy (TMA engine) stages the whole row tile
-      const uint32_t bytes = (uint32_t)rows * d.D * 4u;
-      mbar_arrive_expect_tx(&s_bar, bytes);
-      bulk_g2s(sm, vis_f + (size_t)r0 * d.D, bytes, &s_bar);
+  if (warp == 0) {  // ordered compaction of the live columns
+    int n = 0;
+    for (int c0 = 0; c0 < d.NQ; c0 += 32) {
+      const int c = c0 + lane;
+      const bool lv = c < d.NQ && (c % d.Ne) < __ldg(p.lens + c / d.Ne);
+      const unsigned bal = __ballot_sync(0xffffffffu, lv);
+      const int pos = n + __popc(bal & ((1u << lane) - 1u));
+      if (lv && pos < kLiveMax) s_live[pos] = c;
+      n += __popc(bal);
     }
-    bool waited = false;
-    for (int k0 = 0; k0 < d.D; k0 += 32 * kKS) {
-      // this chunk's word slices for the warp's 4 columns (overlaps the tile copy)
-      float wv[4][kKS];
+    if (lane == 0) s_nlive = n;
+  }
+  __syncthreads();
+  const int nlive = s_nlive;
+
+  if (chunk == 0) {
+    // masked column: every entry is 0 after masked_fill_ -> max 0 at index 0 (model.py:551,612)
+    for (int c = tid; c < d.NQ; c += kFwdThreads)
+      if ((c % d.Ne) >= __ldg(p.lens + c / d.Ne)) {
+        p.D_sim[(size_t)f * d.NQ + c] = 0.f;
+        p.D_ind[(size_t)f * d.NQ + c] = 0ll;
+      }
+  }
+
+  // this CTA serves live-column chunks chunk, chunk + col_chunks, ... of frame f
+  {
+    const int cgp = warp & 1, rg = warp >> 1;
+    uint32_t parity = 0;
+    int tile_in_smem = 0;  // row tile currently staged (the prologue loaded tile 0)
+    bool pending = true;   // a bulk copy has been issued and not yet waited for
+    for (int first = chunk * kColsPerCta; first < nlive; first += p.col_chunks * kColsPerCta) {
+      int col[4];
+      bool live[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float* wr = p.word + (size_t)min(c_base + j, d.NQ - 1) * d.D + k0;
-#pragma unroll
-        for (int i = 0; i < kKS; ++i) {
-          const int k = lane + 32 * i;
-          wv[j][i] = (live[j] && k0 + k < d.D) ? __ldg(wr + k) : 0.f;
-        }
+        const int li = first + cgp * 4 + j;
+        live[j] = li < nlive;
+        col[j] = s_live[min(li, nlive - 1)];
       }
-      if (!waited) {
-        mbar_wait(&s_bar, parity);
-        parity ^= 1u;
-        waited = true;
-      }
-      if (!any_live) break;
-      const bool last_chunk = k0 + 32 * kKS >= d.D;
-      for (int r = 0; r < rows; ++r) {
-        const float* vr = sm + (size_t)r * d.D + k0;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < kKS; ++i) {
-          const int k = lane + 32 * i;
-          const float v = (k0 + k < d.D) ? vr[k] : 0.f;
-          a0 = fmaf(v, wv[0][i], a0);
-          a1 = fmaf(v, wv[1][i], a1);
-          a2 = fmaf(v, wv[2][i], a2);
-          a3 = fmaf(v, wv[3][i], a3);
-        }
-        float tot = reduce4(a0, a1, a2, a3, lane);
-        if (d.D > 32 * kKS) {
-          // multi-chunk D: partial sums are parked in shared memory after the row tile
-          float* part = sm + (size_t)kRowTile * d.D + (size_t)(warp * 4 + (lane >> 3)) * kRowTile + r;
-          if ((lane & 7) == 0) {
-            if (k0 > 0) tot += *part;
-            *part = tot;
+      // best (value, row) of this lane's (row slot, column) = (lane>>3, (lane>>1)&3)
+      float best = -INFINITY;
+      int best_r = 0x7fffffff;
+      for (int r0 = 0; r0 < d.Nb; r0 += kRowTile) {
+        const int rows = min(kRowTile, d.Nb - r0);
+        if (tile_in_smem != r0) {
+          __syncthreads();  // previous tile consumed
+          if (tid == 0) {
+            const uint32_t bytes = (uint32_t)rows * d.D * 4u;
+            mbar_arrive_expect_tx(&s_bar, bytes);
+            bulk_g2s(sm, vis_f + (size_t)r0 * d.D, bytes, &s_bar);
           }
-          __syncwarp();
-          if (!last_chunk) continue;
-          tot = *part;
+          tile_in_smem = r0;
+          pending = true;
         }
-        if (tot > best) {  // strict '>': first maximal box wins (torch.max(dim) tie rule)
-          best = tot;
-          best_r = r0 + r;
+        // this warp's rows inside the tile: contiguous block of <= 8 rows, two batches of 4
+        const int per = (rows + 3) >> 2;
+        const int rb = rg * per, re = min(rows, rb + per);
+        float acc[2][16];
+#pragma unroll
+        for (int bt = 0; bt < 2; ++bt)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[bt][i] = 0.f;
+        for (int k0 = 0; k0 < d.D; k0 += 32 * kKS) {
+          // this chunk's word slices for the warp's 4 columns (overlaps the tile copy)
+          float wv[4][kKS];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float* wr = p.word + (size_t)col[j] * d.D + k0;
+#pragma unroll
+            for (int i = 0; i < kKS; ++i) {
+              const int k = lane + 32 * i;
+              wv[j][i] = (live[j] && k0 + k < d.D) ? __ldg(wr + k) : 0.f;
+            }
+          }
+          if (pending) {
+            mbar_wait(&s_bar, parity);
+            parity ^= 1u;
+            pending = false;
+          }
+          if (!live[0]) break;
+#pragma unroll
+          for (int bt = 0; bt < 2; ++bt) {
+            if (rb + 4 * bt >= re) break;
+            const float* v0 = sm + (size_t)min(rb + 4 * bt + 0, rows - 1) * d.D + k0;
+            const float* v1 = sm + (size_t)min(rb + 4 * bt + 1, rows - 1) * d.D + k0;
+            const float* v2 = sm + (size_t)min(rb + 4 * bt + 2, rows - 1) * d.D + k0;
+            const float* v3 = sm + (size_t)min(rb + 4 * bt + 3, rows - 1) * d.D + k0;
+#pragma unroll
+            for (int i = 0; i < kKS; ++i) {
+              const int k = lane + 32 * i;
+              const bool ok = k0 + k < d.D;
+              const float x0 = ok ? v0[k] : 0.f, x1 = ok ? v1[k] : 0.f;
+              const float x2 = ok ? v2[k] : 0.f, x3 = ok ? v3[k] : 0.f;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                acc[bt][0 + j] = fmaf(x0, wv[j][i], acc[bt][0 + j]);
+                acc[bt][4 + j] = fmaf(x1, wv[j][i], acc[bt][4 + j]);
+                acc[bt][8 + j] = fmaf(x2, wv[j][i], acc[bt][8 + j]);
+                acc[bt][12 + j] = fmaf(x3, wv[j][i], acc[bt][12 + j]);
+              }
+            }
+          }
+        }
+        if (live[0]) {
+#pragma unroll
+          for (int bt = 0; bt < 2; ++bt) {
+            if (rb + 4 * bt >= re) break;
+            const float tot = reduce16(acc[bt], lane);
+            const int r = rb + 4 * bt + (lane >> 3);  // row slot = value index >> 2
+            // ascending rows per lane: strict '>' keeps the first maximal box (torch.max(dim))
+            if (r < re && tot > best) {
+              best = tot;
+              best_r = r0 + r;
+            }
+          }
         }
       }
+      // combine the 4 row groups x 4 row slots of every column: max value, ties -> lowest row
+      if ((lane & 1) == 0) {
+        const int j = (lane >> 1) & 3, slot = lane >> 3;
+        s_best[cgp * 4 + j][rg * 4 + slot] = best;
+        s_besti[cgp * 4 + j][rg * 4 + slot] = best_r;
+      }
+      __syncthreads();
+      if (tid < kColsPerCta && first + tid < nlive) {
+        float bv = s_best[tid][0];
+        int bi = s_besti[tid][0];
+#pragma unroll
+        for (int g = 1; g < 16; ++g) {
+          const float v = s_best[tid][g];
+          const int vi = s_besti[tid][g];
+          if (v > bv || (v == bv && vi < bi)) {
+            bv = v;
+            bi = vi;
+          }
+        }
+        const int c = s_live[first + tid];
+        p.D_sim[(size_t)f * d.NQ + c] = bv;
+        p.D_ind[(size_t)f * d.NQ + c] = (long long)bi;
+      }
+      __syncthreads();  // s_best is reused by the next chunk
     }
-  }
-  {
-    const int c = my_col;
-    if ((lane & 7) == 0 && c < d.NQ) {
-      const bool is_live = (c % d.Ne) < __ldg(p.lens + c / d.Ne);
-      // masked column: every entry is 0 after masked_fill_ -> max 0 at index 0 (model.py:551,612)
-      p.D_sim[(size_t)f * d.NQ + c] = is_live ? best : 0.f;
-      p.D_ind[(size_t)f * d.NQ + c] = is_live ? (long long)best_r : 0ll;
-    }
+    if (pending) mbar_wait(&s_bar, parity);  // never leave a bulk copy in flight
   }
 
   // ---- chain: last CTA of the segment runs P2, last segment runs P3
-  __threadfence();
+  if (blockIdx.x == 0) TRACE(1);
   __syncthreads();
-  if (tid == 0) s_ticket = atomicAdd(w.seg_cnt + a, 1);
+  if (tid == 0) s_ticket = ticket_acq_rel(w.seg_cnt + a);
   __syncthreads();
+  if (blockIdx.x == 0) TRACE(2);
   if (s_ticket != d.Ns * p.col_chunks - 1) return;
-  __threadfence();
-  phase2_segment(p, w, a, sm);
-  __threadfence();
+  TRACE(16 + a * 8 + 0);
+  phase2_segment(p, w, a);
+  TRACE(16 + a * 8 + 6);
   __syncthreads();
   if (tid == 0) {
     w.seg_cnt[a] = 0;  // leave the counter clean for the next launch
-    s_ticket = atomicAdd(w.done_cnt, 1);
+    s_ticket = ticket_acq_rel(w.done_cnt);
   }
   __syncthreads();
+  TRACE(16 + a * 8 + 7);
   if (s_ticket != d.Na - 1) return;
-  __threadfence();
-  phase3_final(p, w, sm);
+  TRACE(120);
+  phase3_final(p, w);
+  TRACE(125);
   if (tid == 0) *w.done_cnt = 0;
 }
 
@@ -290,36 +387,130 @@ __device__ __forceinline__ ColStat col_stat_smem(const float* __restrict__ Sblk,
   return st;
 }
 
+// 4x4 block of the Gram matrix of the staged rows: M[ra+i][rb+j] = x_{ra+i} . x_{rb+j}.
+// Lanes split k (128-bit LDS), 16 independent accumulators, one reduce16.
+__device__ __forceinline__ void gram_block(const float* rows_sm, int D, int nrows, int ra, int rb,
+                                           float* M, int lane) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  const int n4 = D >> 2;
+  const float4* pa[4];
+  const float4* pb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    pa[i] = reinterpret_cast<const float4*>(rows_sm + (size_t)min(ra + i, nrows - 1) * D);
+    pb[i] = reinterpret_cast<const float4*>(rows_sm + (size_t)min(rb + i, nrows - 1) * D);
+  }
+  for (int k0 = 0; k0 < n4; k0 += 64) {  // 2 float4 per lane per row per step
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = k0 + lane + 32 * u;
+      float4 xa[4], xb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xa[i] = k < n4 ? pa[i][k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        xb[i] = k < n4 ? pb[i][k] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = acc[i * 4 + j];
+          t = fmaf(xa[i].x, xb[j].x, t);
+          t = fmaf(xa[i].y, xb[j].y, t);
+          t = fmaf(xa[i].z, xb[j].z, t);
+          t = fmaf(xa[i].w, xb[j].w, t);
+          acc[i * 4 + j] = t;
+        }
+    }
+  }
+  const float tot = reduce16(acc, lane);
+  if ((lane & 1) == 0) {
+    const int i = lane >> 3, j = (lane >> 1) & 3;
+    if (ra + i < nrows && rb + j < nrows) {
+      M[(ra + i) * kRowTile + rb + j] = tot;
+      M[(rb + j) * kRowTile + ra + i] = tot;
+    }
+  }
+}
+
 // P2: frame attention + Sf for segment a; clustering partials (train).
 // Everything the phase needs from other CTAs (the segment's Ns x NQ block of D_sim / D_ind) is
-// pulled into shared memory with ONE round of independent L2 loads.
-__device__ void phase2_segment(const FwdParams& p, const Ws& w, int a, float* sm) {
+// pulled into shared memory with ONE round of independent L2 loads, overlapped with the bulk copy
+// of the vis rows the clustering loss reads.
+__device__ void phase2_segment(const FwdParams& p, const Ws& w, int a) {
+  // same dynamic shared memory as the kernel (declared here so that loads compile to LDS)
+  extern __shared__ __align__(16) float sm[];
   const Dims& d = p.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int blk = d.Ns * d.NQ;
-  float* Sblk = sm;                                   // [Ns][NQ]
-  int* Iblk = reinterpret_cast<int*>(sm + blk);       // [Ns][NQ]
-  float* c_mn = sm + 2 * blk;                         // [NQ]
+  const int staged = p.train ? min(d.Nb, kRowTile) : 0;  // vis rows 0..staged-1 live in smem
+  const bool all_staged = staged == d.Nb;
+  float* rows_sm = sm;                                // [staged][D]
+  float* Sblk = sm + (size_t)staged * d.D;            // [Ns][NQ]
+  int* Iblk = reinterpret_cast<int*>(Sblk + blk);     // [Ns][NQ]
+  float* c_mn = Sblk + 2 * blk;                       // [NQ]
   float* c_iden = c_mn + d.NQ;                        // [NQ] 1/den
-  float* inv = c_iden + d.NQ;                         // [Ne][Ns] 1/(||x||+eps) of the picked rows
+  float* inv = c_iden + d.NQ;                         // [max(Nb, kRowTile)] 1/(||x_r||+eps)
+  float* M = inv + max(d.Nb, kRowTile);               // [kRowTile][kRowTile] Gram of staged rows
+  __shared__ __align__(8) uint64_t s_bar2;
+  __shared__ int s_len[256];  // entities_length[a'] (first 256 segments; others re-read)
+  __shared__ float s_red[kFwdWarps];
+  __shared__ int s_redi[kFwdWarps];
   __syncthreads();
+  if (tid == 0 && staged > 0) {
+    // The clustering loss gathers rows WITHOUT their (segment, frame) offset (SURVEY.md fact
+    // 0.7): only rows 0..Nb-1 of vis_feats are ever read.  One bulk copy brings them on chip.
+    mbar_init(&s_bar2, 1);
+    fence_mbar_init();
+    const uint32_t bytes = (uint32_t)staged * d.D * 4u;
+    mbar_arrive_expect_tx(&s_bar2, bytes);
+    bulk_g2s(rows_sm, p.vis, bytes, &s_bar2);
+  }
+  for (int i = tid; i < min(d.Na, 256); i += kFwdThreads) s_len[i] = __ldg(p.lens + i);
   const float* gS = p.D_sim + (size_t)a * blk;
   const long long* gI = p.D_ind + (size_t)a * blk;
-  for (int i = tid; i < blk; i += kFwdThreads) {
-    Sblk[i] = __ldcg(gS + i);
-    Iblk[i] = (int)__ldcg(gI + i);
+  for (int i0 = 0; i0 < blk; i0 += 4 * kFwdThreads) {  // 4 independent loads per thread in flight
+    float sv[4];
+    int iv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * kFwdThreads + tid;
+      sv[j] = i < blk ? __ldcg(gS + i) : 0.f;
+      iv[j] = i < blk ? (int)__ldcg(gI + i) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * kFwdThreads + tid;
+      if (i < blk) {
+        Sblk[i] = sv[j];
+        Iblk[i] = iv[j];
+      }
+    }
   }
   __syncthreads();
+  TRACE(16 + a * 8 + 1);
   for (int c = tid; c < d.NQ; c += kFwdThreads) {
     const ColStat st = col_stat_smem(Sblk, c, d.Ns, d.NQ);
     c_mn[c] = st.mn;
     c_iden[c] = 1.f / st.den;
   }
+  if (p.train && all_staged) {
+    // Gram matrix of the Nb candidate rows, 4x4 blocks dealt to the warps (upper triangle)
+    mbar_wait(&s_bar2, 0);
+    const int nb4 = (staged + 3) >> 2;
+    int idx = 0;
+    for (int bi = 0; bi < nb4; ++bi)
+      for (int bj = bi; bj < nb4; ++bj, ++idx)
+        if ((idx & (kFwdWarps - 1)) == warp) gram_block(rows_sm, d.D, staged, bi * 4, bj * 4, M, lane);
+  }
   __syncthreads();
+  TRACE(16 + a * 8 + 2);
   // Sf[a,s,a'] = sum_e S*S_att / div[a']   (model.py:583-593); thread per (s, a')
   for (int i = tid; i < d.Ns * d.Na; i += kFwdThreads) {
     const int s = i / d.Na, a2 = i % d.Na;
-    const int len = __ldg(p.lens + a2);
+    const int len = a2 < 256 ? s_len[a2] : __ldg(p.lens + a2);
     float acc = 0.f;
     for (int e = 0; e < len; ++e) {
       const int c = a2 * d.Ne + e;
@@ -330,127 +521,173 @@ __device__ void phase2_segment(const FwdParams& p, const Ws& w, int a, float* sm
   }
   if (!p.train) return;
 
-  // clustering loss of segment a (model.py:553-577).  Rows come from frame 0 of segment 0: the
-  // box index is used without its (segment, frame) offset.
-  const int len = __ldg(p.lens + a);
-  for (int i = warp; i < len * d.Ns; i += kFwdWarps) {  // norms, warp per picked row
-    const int e = i / d.Ns, s = i % d.Ns;
-    const float* x = p.vis + (size_t)Iblk[s * d.NQ + a * d.Ne + e] * d.D;
-    const float acc = warp_dot(x, x, d.D, lane);
-    if (lane == 0) inv[i] = 1.f / (sqrtf(acc) + kEps);
-  }
-  __syncthreads();
-  // Gram entries s<t of every entity; G is symmetric so the ordered sum / count double
+  // clustering loss of segment a (model.py:553-577)
+  const int len = a < 256 ? s_len[a] : __ldg(p.lens + a);
+  const int pairs = d.Ns * (d.Ns - 1) / 2;
   float gsum = 0.f;
   int gcnt = 0;
-  const int pairs = d.Ns * (d.Ns - 1) / 2;
-  for (int i = warp; i < len * pairs; i += kFwdWarps) {
-    const int e = i / pairs;
-    int q = i % pairs, s = 0;
-    while (q >= d.Ns - 1 - s) {
-      q -= d.Ns - 1 - s;
-      ++s;
-    }
-    const int t = s + 1 + q;
-    const int c = a * d.Ne + e;
-    const float* xs = p.vis + (size_t)Iblk[s * d.NQ + c] * d.D;
-    const float* xt = p.vis + (size_t)Iblk[t * d.NQ + c] * d.D;
-    const float acc = warp_dot(xs, xt, d.D, lane);
-    const float ss = (Sblk[s * d.NQ + c] - c_mn[c]) * c_iden[c];
-    const float st = (Sblk[t * d.NQ + c] - c_mn[c]) * c_iden[c];
-    const float dot = acc * (ss * inv[e * d.Ns + s]) * (st * inv[e * d.Ns + t]);
-    const float g = 1.f - dot;
-    if (lane == 0) {
+  if (all_staged) {
+    for (int r = tid; r < d.Nb; r += kFwdThreads) inv[r] = 1.f / (sqrtf(M[r * kRowTile + r]) + kEps);
+    __syncthreads();
+    TRACE(16 + a * 8 + 4);
+    // Gram entries s<t of every entity (G is symmetric: the ordered sum / count double);
+    // thread per (entity, pair), everything is a table lookup now
+    for (int i = tid; i < len * pairs; i += kFwdThreads) {
+      const int e = i / pairs;
+      int q = i % pairs, s = 0;
+      while (q >= d.Ns - 1 - s) {
+        q -= d.Ns - 1 - s;
+        ++s;
+      }
+      const int t = s + 1 + q;
+      const int c = a * d.Ne + e;
+      const int rs = Iblk[s * d.NQ + c], rt = Iblk[t * d.NQ + c];
+      const float ss = (Sblk[s * d.NQ + c] - c_mn[c]) * c_iden[c];
+      const float st = (Sblk[t * d.NQ + c] - c_mn[c]) * c_iden[c];
+      const float g = 1.f - M[rs * kRowTile + rt] * (ss * inv[rs]) * (st * inv[rt]);
       gsum += 2.f * g;
       gcnt += (g != 0.f) ? 2 : 0;
     }
+  } else {
+    // Nb > kRowTile: rows beyond the staged tile are read from global memory, warp per dot
+    if (staged > 0) mbar_wait(&s_bar2, 0);
+    auto row_ptr = [&](int r) -> const float* {
+      return r < staged ? rows_sm + (size_t)r * d.D : p.vis + (size_t)r * d.D;
+    };
+    for (int r = warp; r < d.Nb; r += kFwdWarps) {
+      const float acc = warp_dot(row_ptr(r), row_ptr(r), d.D, lane);
+      if (lane == 0) inv[r] = 1.f / (sqrtf(acc) + kEps);
+    }
+    __syncthreads();
+    for (int i = warp; i < len * pairs; i += kFwdWarps) {
+      const int e = i / pairs;
+      int q = i % pairs, s = 0;
+      while (q >= d.Ns - 1 - s) {
+        q -= d.Ns - 1 - s;
+        ++s;
+      }
+      const int t = s + 1 + q;
+      const int c = a * d.Ne + e;
+      const int rs = Iblk[s * d.NQ + c], rt = Iblk[t * d.NQ + c];
+      const float acc = warp_dot(row_ptr(rs), row_ptr(rt), d.D, lane);
+      const float ss = (Sblk[s * d.NQ + c] - c_mn[c]) * c_iden[c];
+      const float st = (Sblk[t * d.NQ + c] - c_mn[c]) * c_iden[c];
+      const float g = 1.f - acc * (ss * inv[rs]) * (st * inv[rt]);
+      if (lane == 0) {
+        gsum += 2.f * g;
+        gcnt += (g != 0.f) ? 2 : 0;
+      }
+    }
   }
-  __shared__ float s_gsum[kFwdWarps];
-  __shared__ int s_gcnt[kFwdWarps];
+  TRACE(16 + a * 8 + 5);
+  gsum = warp_sum(gsum);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gcnt += __shfl_xor_sync(0xffffffffu, gcnt, o);
   if (lane == 0) {
-    s_gsum[warp] = gsum;
-    s_gcnt[warp] = gcnt;
+    s_red[warp] = gsum;
+    s_redi[warp] = gcnt;
   }
   __syncthreads();
   if (tid == 0) {
     float ts = 0.f;
     int tc = 0;
     for (int k = 0; k < kFwdWarps; ++k) {
-      ts += s_gsum[k];
-      tc += s_gcnt[k];
+      ts += s_red[k];
+      tc += s_redi[k];
     }
     w.vsum[a] = ts;
     w.vcnt[a] = tc;
   }
 }
 
-// P3: hinge ranking loss over all segments (model.py:594-606) and its gradient w.r.t. Sf
-__device__ void phase3_final(const FwdParams& p, const Ws& w, float* sm) {
+// P3: hinge ranking loss over all segments (model.py:594-606) and its gradient w.r.t. Sf.
+// Gather form, thread per Sf element (p, s, q): no atomics, one round of L2 loads.
+__device__ void phase3_final(const FwdParams& p, const Ws& w) {
+  extern __shared__ __align__(16) float sm[];
   const Dims& d = p.d;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = d.Na * d.Ns * d.Na;
-  __shared__ float s_part[kFwdThreads];
-  float* Sf = sm;       // [Na][Ns][Na]
-  float* hg = sm + n;   // [Na][Ns][Na]
+  float* Sf = sm;  // [Na][Ns][Na]
+  __shared__ float s_part[kFwdWarps];
+  __shared__ float s_vs[kFwdWarps];
+  __shared__ int s_vc[kFwdWarps];
   __syncthreads();
-  for (int i = tid; i < n; i += kFwdThreads) {
-    Sf[i] = __ldcg(w.Sf + i);
-    hg[i] = 0.f;
+  float vs = 0.f;
+  int vc = 0;
+  if (p.train)
+    for (int a = tid; a < d.Na; a += kFwdThreads) {
+      vs += __ldcg(w.vsum + a);
+      vc += __ldcg(w.vcnt + a);
+    }
+  for (int i0 = 0; i0 < n; i0 += 4 * kFwdThreads) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * kFwdThreads + tid;
+      v[j] = i < n ? __ldcg(w.Sf + i) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * kFwdThreads + tid;
+      if (i < n) Sf[i] = v[j];
+    }
+  }
+  vs = warp_sum(vs);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vc += __shfl_xor_sync(0xffffffffu, vc, o);
+  if (lane == 0) {
+    s_vs[warp] = vs;
+    s_vc[warp] = vc;
   }
   __syncthreads();
-  // frame_score[a,s] = mean_a'' relu(Sf[a'',s,a] - d[a,s] + Delta) + mean_a' relu(Sf[a,s,a'] - d[a,s] + Delta)
+  TRACE(121);
+  // frame_score[a,s] = mean_o relu(Sf[o,s,a] - d[a,s] + Delta) + mean_o relu(Sf[a,s,o] - d[a,s] + Delta)
+  // summed over (a,s) this is sum over elements (p,s,q) of relu(x - d[q,s] + D) + relu(x - d[p,s] + D)
   float part = 0.f;
   const float inv_na = 1.f / (float)d.Na;
   const float gscale = 10.f / (float)(d.Na * d.Ns) * inv_na;  // d(margin)/d(relu term)
-  for (int i = tid; i < d.Na * d.Ns; i += kFwdThreads) {
-    const int a = i / d.Ns, s = i % d.Ns;
-    const float dg = Sf[(a * d.Ns + s) * d.Na + a];
-    float t1 = 0.f, t2 = 0.f;
-    float gd = 0.f;  // gradient reaching d[a,s]
-    for (int o = 0; o < d.Na; ++o) {
-      const float v1 = (Sf[(o * d.Ns + s) * d.Na + a] - dg) + p.Delta;
-      const float v2 = (Sf[(a * d.Ns + s) * d.Na + o] - dg) + p.Delta;
-      if (v1 > 0.f) {
-        t1 += v1;
-        atomicAdd(hg + (o * d.Ns + s) * d.Na + a, gscale);
-        gd -= gscale;
+  for (int i = tid; i < n; i += kFwdThreads) {
+    const int q = i % d.Na, s = (i / d.Na) % d.Ns, pp = i / (d.Na * d.Ns);
+    const float x = Sf[i];
+    const float dq = Sf[(q * d.Ns + s) * d.Na + q], dp = Sf[(pp * d.Ns + s) * d.Na + pp];
+    const float vA = (x - dq) + p.Delta;  // video pp as a negative for text q
+    const float vB = (x - dp) + p.Delta;  // text q as a negative for video pp
+    part += fmaxf(vA, 0.f) + fmaxf(vB, 0.f);
+    float g = gscale * ((vA > 0.f ? 1.f : 0.f) + (vB > 0.f ? 1.f : 0.f));
+    if (pp == q) {  // d[q,s] enters every hinge of row/column q with a minus sign
+      int cnt = 0;
+      for (int o = 0; o < d.Na; ++o) {
+        cnt += ((Sf[(o * d.Ns + s) * d.Na + q] - dq) + p.Delta > 0.f) ? 1 : 0;
+        cnt += ((Sf[(q * d.Ns + s) * d.Na + o] - dq) + p.Delta > 0.f) ? 1 : 0;
       }
-      if (v2 > 0.f) {
-        t2 += v2;
-        atomicAdd(hg + (a * d.Ns + s) * d.Na + o, gscale);
-        gd -= gscale;
-      }
+      g -= gscale * (float)cnt;
     }
-    atomicAdd(hg + (a * d.Ns + s) * d.Na + a, gd);
-    part += t1 * inv_na + t2 * inv_na;
+    w.hgrad[i] = g;
   }
-  s_part[tid] = part;
+  part = warp_sum(part);
+  if (lane == 0) s_part[warp] = part;
   __syncthreads();
-  for (int i = tid; i < n; i += kFwdThreads) w.hgrad[i] = hg[i];
-  if (tid < 32) {  // deterministic tree over the 256 partials
-    float v = 0.f;
-    for (int k = tid; k < kFwdThreads; k += 32) v += s_part[k];
-    v = warp_sum(v);
-    if (tid == 0) {
-      const float mean_fs = v / (float)(d.Na * d.Ns);
-      float loss = mean_fs * 10.f;
-      float vis_loss = 0.f, dem = 0.f;
-      if (p.train) {
-        float ts = 0.f;
-        int tc = 0;
-        for (int a = 0; a < d.Na; ++a) {
-          ts += __ldcg(w.vsum + a);
-          tc += __ldcg(w.vcnt + a);
-        }
-        dem = (float)tc;
-        vis_loss = ts / dem;  // NaN when nothing is unmasked, like the reference (model.py:576-577)
-        loss = (mean_fs + p.vis_lam * vis_loss) * 10.f;
-      }
-      w.scal[0] = vis_loss;
-      w.scal[1] = dem;
-      w.scal[2] = mean_fs;
-      *p.loss = loss;
+  TRACE(122);
+  if (tid == 0) {
+    float fs = 0.f, ts = 0.f;
+    int tc = 0;
+    for (int k = 0; k < kFwdWarps; ++k) {
+      fs += s_part[k];
+      ts += s_vs[k];
+      tc += s_vc[k];
     }
+    const float mean_fs = fs * inv_na / (float)(d.Na * d.Ns);
+    float loss = mean_fs * 10.f;
+    float vis_loss = 0.f, dem = 0.f;
+    if (p.train) {
+      dem = (float)tc;
+      vis_loss = ts / dem;  // NaN when nothing is unmasked, like the reference (model.py:576-577)
+      loss = (mean_fs + p.vis_lam * vis_loss) * 10.f;
+    }
+    w.scal[0] = vis_loss;
+    w.scal[1] = dem;
+    w.scal[2] = mean_fs;
+    *p.loss = loss;
   }
 }
 
@@ -741,6 +978,12 @@ bool make_dims(int Na, int Ns, int Nb, int Ne, int D, Dims* d) {
 
 using namespace nafae;
 
+#ifdef NAFAE_TRACE
+NAFAE_API int nafae_debug_read_trace(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(unsigned long long) * 256);
+}
+#endif
+
 NAFAE_API size_t nafae_ground_workspace_bytes(int Na, int Ns, int Nb, int Ne, int D) {
   Dims d;
   if (!make_dims(Na, Ns, Nb, Ne, D, &d)) return 0;
@@ -750,6 +993,7 @@ NAFAE_API size_t nafae_ground_workspace_bytes(int Na, int Ns, int Nb, int Ne, in
 static int check_ground_args(const Dims& d, const void* ws, size_t ws_bytes, int train) {
   NAFAE_REQUIRE(d.D % 4 == 0, "ground: D must be a multiple of 4, got %d", d.D);
   NAFAE_REQUIRE(d.Ne <= 16, "ground: max_ent_len %d > 16 not supported", d.Ne);
+  NAFAE_REQUIRE(d.NQ <= kLiveMax, "ground: Na*Ne = %d exceeds %d", d.NQ, kLiveMax);
   NAFAE_REQUIRE(!train || d.Ns <= kMaxNsLocal,
                 "ground: train phase supports at most %d frames per segment", kMaxNsLocal);
   NAFAE_REQUIRE((long long)d.F * d.Nb * (long long)d.D < (1ll << 31), "ground: vis_feats too large");
@@ -783,12 +1027,18 @@ NAFAE_API int nafae_ground_forward(const float* vis_feats, const float* word_fea
   p.Delta = Delta;
   p.vis_lam = vis_lam;
   p.train = train ? 1 : 0;
-  p.col_chunks = ceil_div(d.NQ, kColsPerCta);
+  // CTAs per frame: enough to fill the GPU once, never more than the column chunks there can be
+  {
+    int g = ceil_div(sm_count(), d.F);
+    const int gmax = ceil_div(d.NQ, kColsPerCta);
+    p.col_chunks = g < 1 ? 1 : (g > gmax ? gmax : g);
+  }
   // shared memory: row tile (+ parked partial sums when D > 512), reused by P2's small tables
   size_t smem = (size_t)kRowTile * d.D * 4;
-  if (d.D > 32 * kKS) smem += (size_t)kFwdWarps * 4 * kRowTile * 4;
-  const size_t p2 = ((size_t)2 * d.Ns * d.NQ + 2 * (size_t)d.NQ + (size_t)d.Ne * d.Ns) * 4;
-  const size_t p3 = (size_t)2 * d.Na * d.Ns * d.Na * 4;
+  const size_t p2 = ((size_t)(train ? (d.Nb < kRowTile ? d.Nb : kRowTile) : 0) * d.D +
+                     (size_t)2 * d.Ns * d.NQ + 2 * (size_t)d.NQ + (size_t)(d.Nb > kRowTile ? d.Nb : kRowTile) +
+                     (size_t)kRowTile * kRowTile) * 4;
+  const size_t p3 = (size_t)d.Na * d.Ns * d.Na * 4;
   if (p2 > smem) smem = p2;
   if (p3 > smem) smem = p3;
   NAFAE_REQUIRE(smem <= 200 * 1024, "ground: D=%d / Ns=%d need too much shared memory", d.D, d.Ns);

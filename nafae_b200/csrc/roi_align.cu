@@ -325,10 +325,14 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
   // -------------------------------------------------------------- consumer warps ----
   // RoIs whose batch index is outside [0, B): defined as all-zero rows (CTA 0 writes them)
   if (blockIdx.x == 0) {
-    for (int r = warp; r < p.R; r += kConsWarps) {
-      const int b = (int)p.rois[(size_t)r * 5];
-      if (b < 0 || b >= p.B) {
-        float* o = p.top + (size_t)r * p.C * (kOut * kOut);
+    for (int r0 = warp * 32; r0 < p.R; r0 += kConsThreads) {  // one RoI per lane, loads in flight
+      const int r = r0 + lane;
+      const int b = r < p.R ? (int)__ldg(p.rois + (size_t)r * 5) : 0;
+      unsigned bad = __ballot_sync(0xffffffffu, r < p.R && (b < 0 || b >= p.B));
+      while (bad) {
+        const int rr = r0 + __ffs(bad) - 1;
+        bad &= bad - 1;
+        float* o = p.top + (size_t)rr * p.C * (kOut * kOut);
         for (int i = lane; i < p.C * kOut * kOut; i += 32) o[i] = 0.f;
       }
     }
