@@ -26,6 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+HEAD_SMS = 16  # SMs the persistent RoIAlign kernel leaves to the overlapped head kernels
 METRIC = "video segments/sec (grounding head fwd+bwd)"
 UNIT = "segments/s"
 
@@ -39,6 +40,10 @@ def parse_args():
     ap.add_argument("--cfg", default="cfg2", choices=["cfg2", "cfg2_real", "cfg4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="run the two halves of a step back to back instead of overlapping the head of "
+                         "batch k with the detector half of batch k+1")
+    ap.add_argument("--reserve-sms", type=int, default=-1)
     return ap.parse_args()
 
 
@@ -217,9 +222,43 @@ def run_ours(args):
         buckets = [parallel.GradBucket(parallel.trainable_grad_elems(), dev, world) for _ in range(2)]
         for st, b in zip(steps, buckets):
             st.grad_word = b.views([(st.NQ, c["D"])])[0]
+    from nafae_b200 import _C
+    from nafae_b200.pipeline import capture_pipelined
+    pipelined = not args.no_pipeline
+    reserve = args.reserve_sms if args.reserve_sms >= 0 else (
+        (HEAD_SMS if pipelined else 0) + (parallel.COMM_SMS if world > 1 else 0))
+    _C.lib.nafae_set_reserved_sms(reserve)
+    side = torch.cuda.Stream(dev)
+    comm = torch.cuda.Stream(dev) if world > 1 else None
     for st, hb in zip(steps, host):
         st.load(hb)
-        st.capture()
+        st.run()  # warm-up, produces valid state for the first pipelined replay
+    if world > 1:
+        for b in buckets:
+            dist.all_reduce(b.buf, op=dist.ReduceOp.AVG)  # communicator warm-up
+    torch.cuda.synchronize()
+    graphs = []
+    for j in range(2):
+        # replay j: detector half of set j || head half of set 1-j || all-reduce of the bucket the
+        # head of set j filled in the previous replay
+        def ar_branch(cur, j=j):
+            if world <= 1:
+                return None
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                dist.all_reduce(buckets[j].buf, op=dist.ReduceOp.AVG)
+            return comm
+        if pipelined:
+            graphs.append(capture_pipelined(steps[j], steps[1 - j], side, ar_branch))
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cur = torch.cuda.current_stream()
+                st_comm = ar_branch(cur, 1 - j)
+                steps[j].run()
+                if st_comm is not None:
+                    cur.wait_stream(st_comm)
+            graphs.append(g)
     torch.cuda.synchronize()
 
     def barrier():
@@ -229,15 +268,10 @@ def run_ours(args):
 
     def loop(n):
         for i in range(n):
-            j = i & 1
-            if buckets:
-                buckets[j].wait()
-            steps[j].replay()
-            if buckets:
-                buckets[j].allreduce_async()
-        if buckets:
-            for b in buckets:
-                b.wait()
+            graphs[i & 1].replay()
+        if buckets:  # flush: the last step's gradients are still un-reduced
+            buckets[(n - 1) & 1].allreduce_async()
+            buckets[(n - 1) & 1].wait()
 
     loop(Wm)
     barrier()
@@ -254,8 +288,6 @@ def run_ours(args):
     value = world * K * c["Na"] / (ms_total / 1e3)
 
     # dominant kernel alone, same stream, same alternating inputs (roofline.achieved)
-    from nafae_b200 import _C
-
     def align_only(st):
         _C.check(_C.lib.nafae_roi_align_forward(_C.ptr(st.features), st.scale, st.F, st.R, st.H, st.W,
                                                 st.C, 7, 7, _C.POOL_AVG, _C.ptr(st.rois),
@@ -293,6 +325,8 @@ def run_ours(args):
         for ev in free:
             ev.record()
         Ke = max(10, min(K, 50))
+        _C.lib.nafae_set_reserved_sms(0)
+        e2e_graphs = [st.capture() for st in steps]
 
         def e2e_loop(n):
             for i in range(n):
@@ -302,7 +336,7 @@ def run_ours(args):
                     steps[j].load(pinned[j], non_blocking=True)
                     loaded[j].record(copy_s)
                 comp.wait_event(loaded[j])
-                steps[j].replay()
+                e2e_graphs[j].replay()
                 res[j]["loss"].copy_(steps[j].loss, non_blocking=True)
                 res[j]["D_ind"].copy_(steps[j].D_ind, non_blocking=True)
                 free[j].record(comp)
@@ -344,13 +378,20 @@ def run_ours(args):
                 gpu_launches=K * steps[0].kernels_per_step(),
                 roofline=dict(bound="hbm", kernel="align_pool_fwd_slab", achieved=achieved, peak=peak,
                               unit="GB/s", frac=achieved / peak, traffic=traffic,
-                              kernel_us=kern_us, algorithmic_bytes=ab["total"], peak_source=peak_src,
+                              kernel_us=kern_us, kernel_grid_sms=int(torch.cuda.get_device_properties(dev).multi_processor_count) - reserve,
+                              algorithmic_bytes=ab["total"], peak_source=peak_src,
                               step_frac=(ab["total"] / (ms_total / K * 1e-3) / 1e9) / peak),
                 clocks=clocks)
+    line["config"]["schedule"] = (
+        "software-pipelined: one CUDA graph per step = detector half (proposal tail + RoIAlign) of batch "
+        "k+1 || head half (DVSA fwd+bwd) of batch k%s; %d SMs reserved from the persistent RoIAlign kernel"
+        % (" || gradient all-reduce" if world > 1 else "", reserve)) if pipelined else (
+        "sequential: one CUDA graph per step, five kernels back to back")
     if world > 1:
-        line["config"]["allreduce"] = ("NCCL all-reduce SUM/world per step over a flat fp32 bucket of "
-                                       "%d elems on a side stream, overlapped with the next step"
-                                       % parallel.trainable_grad_elems())
+        line["config"]["allreduce"] = ("NCCL all-reduce (AVG) per step over a flat fp32 bucket of %d elems, "
+                                       "captured as a parallel branch of the NEXT step's CUDA graph "
+                                       "(overlaps its NMS/RoIAlign); %d SMs left free for it"
+                                       % (parallel.trainable_grad_elems(), parallel.COMM_SMS))
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

@@ -46,6 +46,12 @@ typedef struct CUstream_st* cudaStream_t; /* same opaque handle as CUDA driver_t
 int nafae_abi_version(void);
 const char* nafae_last_error(void);
 
+/* Persistent kernels (the RoIAlign slab kernel) launch one CTA per SM.  When a collective runs
+ * concurrently on another stream (data-parallel gradient all-reduce), leave `n` SMs free for its
+ * CTAs so neither kernel waits for the other's residency.  Process-wide, default 0; returns the
+ * previous value.  n is clamped to [0, SMs-1]. */
+int nafae_set_reserved_sms(int n);
+
 /* ------------------------------------------------------------------------------- NMS ---- */
 
 /* Replaces nms_cuda_compute() -- lib/model/nms/src/nms_cuda_kernel.h:5-6 (impl

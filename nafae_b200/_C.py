@@ -25,6 +25,7 @@ c_int, c_float, c_size_t, c_void_p, c_uint = (ctypes.c_int, ctypes.c_float, ctyp
 SIGNATURES = {
     "nafae_abi_version": (c_int, []),
     "nafae_last_error": (ctypes.c_char_p, []),
+    "nafae_set_reserved_sms": (c_int, [c_int]),
     "nms_cuda_compute": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float]),
     "nafae_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nafae_nms_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,

@@ -27,6 +27,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int sm_count();  // cached multiprocessor count of the current device
+int persistent_grid();  // sm_count() minus the SMs reserved for concurrent collectives
 
 // ---------------------------------------------------------------- device side helpers ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

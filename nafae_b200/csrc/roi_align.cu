@@ -507,7 +507,7 @@ int launch_slab(const SlabParams& p, int pool, size_t smem, cudaStream_t stream)
     set_error("roi_align: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     return -(int)e;
   }
-  int grid = sm_count();
+  int grid = persistent_grid();
   if (grid > p.units) grid = p.units;
   kern<<<grid, kSlabThreads, smem, stream>>>(p);
   return launch_status("align_pool_fwd_slab");

@@ -34,7 +34,20 @@ int sm_count() {
   return cached[dev];
 }
 
+static int g_reserved_sms = 0;
+
+int persistent_grid() {
+  int n = sm_count() - g_reserved_sms;
+  return n < 1 ? 1 : n;
+}
+
 }  // namespace nafae
+
+NAFAE_API int nafae_set_reserved_sms(int n) {
+  const int prev = nafae::g_reserved_sms;
+  nafae::g_reserved_sms = n < 0 ? 0 : n;
+  return prev;
+}
 
 NAFAE_API int nafae_abi_version(void) { return NAFAE_B200_ABI_VERSION; }
 NAFAE_API const char* nafae_last_error(void) { return nafae::g_err; }

@@ -13,6 +13,9 @@ import torch
 import torch.distributed as dist
 
 
+COMM_SMS = int(os.environ.get("NAFAE_COMM_SMS", "8"))  # SMs left to the collective while the slab kernel runs
+
+
 def trainable_grad_elems(vis_fc_dim=4096, glove_dim=200, ebd_dim=512):
     return (ebd_dim * vis_fc_dim + ebd_dim) + (ebd_dim * glove_dim + ebd_dim) + 2 * ebd_dim
 
@@ -31,6 +34,11 @@ def init_from_env(backend=None):
         if backend == "nccl":
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
+            # the all-reduce overlaps the persistent RoIAlign kernel: bound the SMs NCCL takes and
+            # keep that many free (see nafae_set_reserved_sms in include/nafae_b200.h)
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(COMM_SMS))
+            from . import _C
+            _C.lib.nafae_set_reserved_sms(COMM_SMS)
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local
 
@@ -73,7 +81,7 @@ class GradBucket(object):
     def allreduce_async(self):
         if self.world <= 1:
             return
-        if self.stream is None:  # CPU / gloo (tests)
+        if self.stream is None:  # CPU / gloo (tests; gloo has no AVG)
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
             self.buf.div_(self.world)
             return
@@ -81,8 +89,7 @@ class GradBucket(object):
         ready.record()
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
-            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
-            self.buf.div_(self.world)
+            dist.all_reduce(self.buf, op=dist.ReduceOp.AVG)  # SUM/world inside NCCL: one kernel
             self._done = torch.cuda.Event()
             self._done.record()
 
@@ -90,3 +97,27 @@ class GradBucket(object):
         if self._done is not None:
             torch.cuda.current_stream().wait_event(self._done)
             self._done = None
+
+
+def capture_step_with_allreduce(step, reduce_bucket, side_stream):
+    """One CUDA graph per training step: the whole hot path of `step` on the capturing stream and,
+    as a parallel branch, the all-reduce (AVG) of `reduce_bucket` -- the gradients the PREVIOUS step
+    produced.  Replaying graph i+1 therefore overlaps step i's gradient all-reduce with step i+1's
+    NMS / RoIAlign inside a single launch; consecutive replays serialise, so a bucket is never
+    rewritten before its all-reduce has finished."""
+    step.run()  # warm up outside capture
+    if reduce_bucket is not None and reduce_bucket.world > 1:
+        dist.all_reduce(reduce_bucket.buf, op=dist.ReduceOp.AVG)  # communicator warm-up
+    torch.cuda.synchronize(step.dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        cur = torch.cuda.current_stream()
+        if reduce_bucket is not None and reduce_bucket.world > 1:
+            side_stream.wait_stream(cur)
+            with torch.cuda.stream(side_stream):
+                dist.all_reduce(reduce_bucket.buf, op=dist.ReduceOp.AVG)
+        step.run()
+        if reduce_bucket is not None and reduce_bucket.world > 1:
+            cur.wait_stream(side_stream)
+    step.graph = g
+    return g

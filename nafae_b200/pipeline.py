@@ -70,12 +70,13 @@ class GroundingStep(object):
                     self.lens))
 
     # -- the step --------------------------------------------------------------------------
-    def run(self, backward=None):
-        """Enqueue the whole step on the current stream.  No host sync, no allocation."""
+    def run_detector(self):
+        """Detector-side half: proposal tail (batched NMS + top-N + padding) -> RoIAlignAvg 7x7.
+        Frozen in NAFAE (model.py:651,673,706-707): independent of the trainable weights, so it may
+        run ahead of / concurrently with the previous batch's head (see `capture_pipelined`)."""
         Na, Ns, Nb, Ne, D = self.dims
         L, P = _C.lib, _C.ptr
         s = _C.stream(self.dev)
-        do_bwd = self.train if backward is None else backward
         with torch.cuda.device(self.dev):
             _C.check(L.nafae_proposal_tail(P(self.proposals), P(self.scores), self.F, self.n,
                                            self.pre, Nb, self.thresh, P(self.rois),
@@ -84,8 +85,16 @@ class GroundingStep(object):
                                                self.W, self.C, 7, 7, _C.POOL_AVG, P(self.rois),
                                                P(self.pooled), 0, None, 0, s),
                      "nafae_roi_align_forward")
-            # (bridge: fc6/fc7 + VisEbd / WordEbd run here in the caller's PyTorch code and
-            #  produce vis_feats / word_feats; they are outside this path)
+
+    def run_head(self, backward=None):
+        """Head half: similarity + losses forward, then backward to dL/dvis_feats, dL/dword_feats.
+        (bridge: fc6/fc7 + VisEbd / WordEbd run between the halves in the caller's PyTorch code and
+        produce vis_feats / word_feats; they are outside this path)"""
+        Na, Ns, Nb, Ne, D = self.dims
+        L, P = _C.lib, _C.ptr
+        s = _C.stream(self.dev)
+        do_bwd = self.train if backward is None else backward
+        with torch.cuda.device(self.dev):
             _C.check(L.nafae_ground_forward(P(self.vis_feats), P(self.word_feats), P(self.lens),
                                             Na, Ns, Nb, Ne, D, self.Delta, self.vis_lam,
                                             int(self.train), P(self.D_ind), P(self.D_sim),
@@ -98,6 +107,11 @@ class GroundingStep(object):
                                                  P(self.D_ind), P(self.D_sim), P(self.grad_vis),
                                                  P(self.grad_word), P(self.ws),
                                                  self.ws.numel() * 4, s), "nafae_ground_backward")
+
+    def run(self, backward=None):
+        """Enqueue the whole step on the current stream.  No host sync, no allocation."""
+        self.run_detector()
+        self.run_head(backward)
 
     def kernels_per_step(self):
         return self.KERNELS_PER_STEP_TRAIN if self.train else self.KERNELS_PER_STEP_EVAL
@@ -114,3 +128,35 @@ class GroundingStep(object):
 
     def replay(self):
         self.graph.replay()
+
+
+def capture_pipelined(det_step, head_step, side_stream, extra_branch=None):
+    """CUDA graph of one software-pipelined training step:
+
+        branch A (capturing stream): detector half of `det_step`   (batch k+1: NMS tail, RoIAlign)
+        branch B (side stream)     : head half of `head_step`      (batch k: DVSA fwd + bwd)
+        branch C (optional)        : `extra_branch()` on its own stream (e.g. gradient all-reduce)
+
+    The detector is frozen in NAFAE, so batch k+1's detector half does not depend on batch k's
+    weight update: the two halves of consecutive batches overlap, like a data loader prefetch.
+    Every replay still executes one full detector half and one full head half; dependencies inside
+    a batch (tail -> RoIAlign, fwd -> bwd) and across replays (graphs serialise) are preserved.
+    Leave a few SMs to branch B/C with `nafae_set_reserved_sms` (the slab kernel is persistent)."""
+    det_step.run_detector()
+    head_step.run_head()
+    torch.cuda.synchronize(det_step.dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        cur = torch.cuda.current_stream()
+        side_stream.wait_stream(cur)
+        streams = [side_stream]
+        with torch.cuda.stream(side_stream):
+            head_step.run_head()
+        if extra_branch is not None:
+            extra_stream = extra_branch(cur)
+            if extra_stream is not None:
+                streams.append(extra_stream)
+        det_step.run_detector()
+        for st in streams:
+            cur.wait_stream(st)
+    return g
