@@ -10,7 +10,7 @@ One "step" = one batch of synthetic YouCookII-shaped segments (BASELINE.json con
 8 segments x 5 frames, 2352 proposals/frame -> NMS 0.7 -> top-20 -> RoIAlignAvg 7x7 over
 512x38x50 conv5 maps -> similarity + ranking/clustering losses forward and backward) through
 
-    proposal_tail -> align_pool_fwd_slab -> ground_fwd -> ground_bwd_cluster -> ground_bwd_main
+    proposal_tail -> align_pool_fwd_slab -> ground_fwd -> ground_bwd
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -228,7 +228,7 @@ def run_ours(args):
     reserve = args.reserve_sms if args.reserve_sms >= 0 else (
         (HEAD_SMS if pipelined else 0) + (parallel.COMM_SMS if world > 1 else 0))
     _C.lib.nafae_set_reserved_sms(reserve)
-    side = torch.cuda.Stream(dev)
+    side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
     comm = torch.cuda.Stream(dev) if world > 1 else None
     for st, hb in zip(steps, host):
         st.load(hb)
@@ -239,8 +239,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     graphs = []
     for j in range(2):
-        # replay j: detector half of set j || head half of set 1-j || all-reduce of the bucket the
-        # head of set j filled in the previous replay
+        # replay j: RoIAlign of set j || proposal tail + head of set 1-j || all-reduce of the bucket
+        # the head of set j filled in the previous replay
         def ar_branch(cur, j=j):
             if world <= 1:
                 return None
@@ -383,8 +383,9 @@ def run_ours(args):
                               step_frac=(ab["total"] / (ms_total / K * 1e-3) / 1e9) / peak),
                 clocks=clocks)
     line["config"]["schedule"] = (
-        "software-pipelined: one CUDA graph per step = detector half (proposal tail + RoIAlign) of batch "
-        "k+1 || head half (DVSA fwd+bwd) of batch k%s; %d SMs reserved from the persistent RoIAlign kernel"
+        "software-pipelined: one CUDA graph per step = RoIAlign of batch k+1 || proposal tail of batch k+2 || "
+        "head (DVSA fwd+bwd) of batch k%s; the detector is frozen, so later batches' NMS/RoIAlign do not "
+        "depend on earlier weight updates; %d SMs reserved from the persistent RoIAlign kernel"
         % (" || gradient all-reduce" if world > 1 else "", reserve)) if pipelined else (
         "sequential: one CUDA graph per step, five kernels back to back")
     if world > 1:

@@ -13,9 +13,9 @@
 //   P2  (last P1 CTA of a segment) per-column min-max frame attention over the segment's frames,
 //       S*S_att summed over entities -> Sf[a,:,:]; clustering loss partials of the segment.
 //   P3  (last P2) hinge terms, frame_score, margin_loss; dL/dSf saved for the backward.
-// Backward = a clustering-gradient kernel (train only) + one kernel with a CTA per frame
-// (dL/dvis rows, dense overwrite) and a CTA per query column (dL/dword): dL/dS_ has at most one
-// non-zero per (frame, column) -- the argmax box -- so both are gather-scale-accumulate sweeps,
+// Backward = ONE kernel with a CTA per frame (dL/dvis rows, dense overwrite), a CTA per query
+// column (dL/dword) and (train) a CTA per entity for the clustering gradient: dL/dS_ has at most
+// one non-zero per (frame, column) -- the argmax box -- so all are gather-scale-accumulate sweeps,
 // not GEMMs.
 //
 // Arithmetic: fp32 FMA, fp32 accumulate.  The contraction is 85 MFLOP at the benchmark shape and
@@ -707,7 +707,7 @@ struct BwdParams {
   int train;
 };
 
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 512;
 constexpr int kMaxNsLocal = 64;  // frames per segment handled by the fused backward
 
 // d(margin_loss)/dS[a,s,c] for all s of one (segment, column), from shared-memory copies:
@@ -742,27 +742,51 @@ __device__ __forceinline__ void col_grad_smem(const float* __restrict__ x, int x
   out[s_mx * os] += g_mx;
 }
 
-// grid F + NQ.  blockIdx < F: dL/dvis rows of frame f (dense overwrite, Nb x D).
-//               else        : dL/dword row of column c.
-// Every cross-CTA input is staged into shared memory with one round of independent loads; the
-// gather loops issue their global loads in batches so they overlap instead of serialising.
-__global__ void __launch_bounds__(kBwdThreads) ground_bwd_main_kernel(const BwdParams p) {
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ONE backward kernel, three kinds of CTAs (512 threads):
+//   blockIdx <  F          : dL/dvis rows of frame f   (dense overwrite, Nb x D)
+//   blockIdx <  F + NQ     : dL/dword row of column c
+//   blockIdx <  F + 2 NQ   : (train) clustering-loss gradient of entity (a, e), added atomically
+//                            into grad_vis rows 0..Nb-1 -- the rows the reference's un-offset
+//                            index_select gathers -- AFTER block 0 (frame 0)
+//                            has written them: block 0 publishes a flag, these CTAs acquire it.
+//                            CTAs are dispatched in blockIdx order, so block 0 is always running
+//                            or finished when a later block spins (decoupled-look-back argument).
+// dL/dS_ has at most one non-zero per (frame, column) -- the argmax box -- so every sweep is a
+// gather-scale-accumulate over <= F*NQ pairs, not a GEMM.  All cross-CTA inputs are staged into
+// shared memory with one round of independent loads; gather loops issue loads in batches.
+__global__ void __launch_bounds__(kBwdThreads, 1) ground_bwd_kernel(const BwdParams p) {
   extern __shared__ __align__(16) float sm[];
   __shared__ int s_nlive;
+  __shared__ int s_ticket;
+  __shared__ __align__(8) uint64_t s_bar;
   const Dims& d = p.d;
   const Ws w = ws_carve(p.ws, d);
-  const int tid = threadIdx.x, lane = tid & 31;
+  int* flag = w.done_cnt + 1;      // frame-0 rows written
+  int* finished = w.done_cnt + 2;  // CTAs that are done (the last one resets the scratch words)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float gout = __ldg(p.gout);
-  if ((int)blockIdx.x < d.F) {
-    const int f = blockIdx.x, a = f / d.Ns, s_me = f % d.Ns;
+  const int bid = blockIdx.x;
+
+  if (bid < d.F) {
+    // ------------------------------------------------------------------ dL/dvis ----
+    const int f = bid, a = f / d.Ns, s_me = f % d.Ns;
     const int blk = d.Ns * d.NQ;
     float* Sblk = sm;                                  // [Ns][NQ]
     float* hg = Sblk + blk;                            // [Ns][Na]
-    float* gtmp = hg + d.Ns * d.Na;                    // [Ns][NQ] per-column gradients
-    int* ridx = reinterpret_cast<int*>(gtmp + blk);    // [NQ]
+    float* gme = hg + d.Ns * d.Na;                     // [NQ] gradient of this frame's S row
+    int* ridx = reinterpret_cast<int*>(gme + d.NQ);    // [NQ]
     int* live = ridx + d.NQ;                           // [NQ] compact list of live columns
     // [kRowTile][D], 16-byte aligned for the float4 write-out
-    float* acc = sm + ((2 * (size_t)blk + (size_t)d.Ns * d.Na + 2 * (size_t)d.NQ + 3) & ~(size_t)3);
+    float* acc = sm + (((size_t)blk + (size_t)d.Ns * d.Na + 3 * (size_t)d.NQ + 3) & ~(size_t)3);
     for (int i = tid; i < blk; i += kBwdThreads) Sblk[i] = __ldg(p.D_sim + (size_t)a * blk + i);
     for (int i = tid; i < d.Ns * d.Na; i += kBwdThreads)
       hg[i] = __ldg(w.hgrad + (size_t)a * d.Ns * d.Na + i);
@@ -775,8 +799,9 @@ __global__ void __launch_bounds__(kBwdThreads) ground_bwd_main_kernel(const BwdP
       if (ridx[c] >= 0) {
         const int a2 = c / d.Ne;
         const int len = __ldg(p.lens + a2);
-        col_grad_smem(Sblk + c, d.NQ, hg + a2, d.Na, d.Ns, gout / (float)(len == 0 ? 1 : len),
-                      gtmp + c, d.NQ);
+        float tmp[kMaxNsLocal];
+        col_grad_smem(Sblk + c, d.NQ, hg + a2, d.Na, d.Ns, gout / (float)(len == 0 ? 1 : len), tmp, 1);
+        gme[c] = tmp[s_me];
       }
     }
     if (tid < 32) {  // ordered compaction of the live columns (warp 0)
@@ -792,26 +817,27 @@ __global__ void __launch_bounds__(kBwdThreads) ground_bwd_main_kernel(const BwdP
     }
     __syncthreads();
     const int nlive = s_nlive;
-    const float* g = gtmp + s_me * d.NQ;
     for (int r0 = 0; r0 < d.Nb; r0 += kRowTile) {
       const int rows = min(kRowTile, d.Nb - r0);
-      for (int i = tid; i < rows * d.D; i += kBwdThreads) acc[i] = 0.f;
+      {
+        float4* z = reinterpret_cast<float4*>(acc);
+        for (int i = tid; i < rows * d.D / 4; i += kBwdThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       __syncthreads();
       for (int k = tid; k < d.D; k += kBwdThreads) {  // thread owns feature k of every row
-        for (int j0 = 0; j0 < nlive; j0 += 8) {
-          float wv[8];
-          int rr[8];
-          float gg[8];
+        for (int j0 = 0; j0 < nlive; j0 += 16) {
+          float wv[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = live[min(j0 + j, nlive - 1)];
-            rr[j] = (j0 + j < nlive) ? ridx[c] - r0 : -1;
-            gg[j] = g[c];
-            wv[j] = __ldg(p.word + (size_t)c * d.D + k);
+          for (int j = 0; j < 16; ++j)
+            wv[j] = __ldg(p.word + (size_t)live[min(j0 + j, nlive - 1)] * d.D + k);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j0 + j < nlive) {
+              const int c = live[j0 + j];
+              const int r = ridx[c] - r0;
+              if (r >= 0 && r < rows) acc[r * d.D + k] = fmaf(gme[c], wv[j], acc[r * d.D + k]);
+            }
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (rr[j] >= 0 && rr[j] < rows) acc[rr[j] * d.D + k] = fmaf(gg[j], wv[j], acc[rr[j] * d.D + k]);
         }
       }
       __syncthreads();
@@ -820,132 +846,136 @@ __global__ void __launch_bounds__(kBwdThreads) ground_bwd_main_kernel(const BwdP
       for (int i = tid; i < rows * d.D / 4; i += kBwdThreads) dst[i] = src[i];
       __syncthreads();
     }
-  } else {
-    const int c = blockIdx.x - d.F, a2 = c / d.Ne;
+    if (bid == 0 && tid == 0) st_release(flag, 1);  // ordered after the CTA's stores by the barrier
+  } else if (bid < d.F + d.NQ) {
+    // ----------------------------------------------------------------- dL/dword ----
+    const int c = bid - d.F, a2 = c / d.Ne;
     float* dst = p.gword + (size_t)c * d.D;
     const int len = __ldg(p.lens + a2);
     if ((c % d.Ne) >= len) {
       for (int k = tid; k < d.D; k += kBwdThreads) dst[k] = 0.f;
-      return;
-    }
-    float* xcol = sm;                                  // [F]
-    float* hcol = xcol + d.F;                          // [F]
-    float* g = hcol + d.F;                             // [F]
-    int* ridx = reinterpret_cast<int*>(g + d.F);       // [F] global vis row of the picked box
-    for (int f = tid; f < d.F; f += kBwdThreads) {
-      xcol[f] = __ldg(p.D_sim + (size_t)f * d.NQ + c);
-      hcol[f] = __ldg(w.hgrad + (size_t)f * d.Na + a2);
-      ridx[f] = f * d.Nb + (int)__ldg(p.D_ind + (size_t)f * d.NQ + c);
-    }
-    __syncthreads();
-    for (int a = tid; a < d.Na; a += kBwdThreads)
-      col_grad_smem(xcol + a * d.Ns, 1, hcol + a * d.Ns, 1, d.Ns, gout / (float)len, g + a * d.Ns, 1);
-    __syncthreads();
-    for (int k = tid; k < d.D; k += kBwdThreads) {
-      float accv = 0.f;
-      for (int f0 = 0; f0 < d.F; f0 += 8) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.vis + (size_t)ridx[min(f0 + j, d.F - 1)] * d.D + k);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (f0 + j < d.F) accv = fmaf(g[f0 + j], v[j], accv);
+    } else {
+      float* xcol = sm;                                  // [F]
+      float* hcol = xcol + d.F;                          // [F]
+      float* g = hcol + d.F;                             // [F]
+      int* ridx = reinterpret_cast<int*>(g + d.F);       // [F] global vis row of the picked box
+      for (int f = tid; f < d.F; f += kBwdThreads) {
+        xcol[f] = __ldg(p.D_sim + (size_t)f * d.NQ + c);
+        hcol[f] = __ldg(w.hgrad + (size_t)f * d.Na + a2);
+        ridx[f] = f * d.Nb + (int)__ldg(p.D_ind + (size_t)f * d.NQ + c);
       }
-      dst[k] = accv;
-    }
-  }
-}
-
-// Clustering-loss gradient, launched AFTER ground_bwd_main_kernel: adds into grad_vis rows
-// 0..Nb-1 (the rows the reference's un-offset index_select gathers).
-// grid NQ, CTA per (a, e); masked entities exit immediately.
-__global__ void __launch_bounds__(kBwdThreads) ground_bwd_cluster_kernel(const BwdParams p) {
-  extern __shared__ __align__(16) float sm[];  // Vsum[D] | simn[Ns] | inv[Ns] | dots[Ns] | row[Ns]
-  const Dims& d = p.d;
-  const Ws w = ws_carve(p.ws, d);
-  const int c = blockIdx.x, a = c / d.Ne, e = c % d.Ne;
-  if (e >= __ldg(p.lens + a)) return;
-  const float dem = __ldg(w.scal + 1);
-  if (!(dem > 0.f)) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* Vsum = sm;
-  float* simn = sm + d.D;
-  float* inv = simn + d.Ns;
-  float* dots = inv + d.Ns;
-  int* row = reinterpret_cast<int*>(dots + d.Ns);
-  for (int s = tid; s < d.Ns; s += kBwdThreads) {
-    simn[s] = __ldg(p.D_sim + (size_t)(a * d.Ns + s) * d.NQ + c);
-    row[s] = (int)__ldg(p.D_ind + (size_t)(a * d.Ns + s) * d.NQ + c);
-  }
-  __syncthreads();
-  float mn = INFINITY, mx = -INFINITY;
-  for (int s = 0; s < d.Ns; ++s) {
-    mn = fminf(mn, simn[s]);
-    mx = fmaxf(mx, simn[s]);
-  }
-  const float iden = 1.f / ((mx - mn) + kEps);
-  __syncthreads();
-  for (int s = tid; s < d.Ns; s += kBwdThreads) simn[s] = (simn[s] - mn) * iden;
-  for (int s = warp; s < d.Ns; s += kBwdThreads / 32) {
-    const float* x = p.vis + (size_t)row[s] * d.D;
-    const float acc = warp_dot(x, x, d.D, lane);
-    if (lane == 0) inv[s] = 1.f / (sqrtf(acc) + kEps);
-  }
-  __syncthreads();
-  for (int k = tid; k < d.D; k += kBwdThreads) {
-    float acc = 0.f;
-    for (int s0 = 0; s0 < d.Ns; s0 += 8) {
-      float xv[8];
+      __syncthreads();
+      for (int a = tid; a < d.Na; a += kBwdThreads)
+        col_grad_smem(xcol + a * d.Ns, 1, hcol + a * d.Ns, 1, d.Ns, gout / (float)len, g + a * d.Ns, 1);
+      __syncthreads();
+      for (int k = tid; k < d.D; k += kBwdThreads) {
+        float accv = 0.f;
+        for (int f0 = 0; f0 < d.F; f0 += 20) {
+          float v[20];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xv[j] = __ldg(p.vis + (size_t)row[min(s0 + j, d.Ns - 1)] * d.D + k);
+          for (int j = 0; j < 20; ++j) v[j] = __ldg(p.vis + (size_t)ridx[min(f0 + j, d.F - 1)] * d.D + k);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (s0 + j < d.Ns) acc += simn[s0 + j] * inv[s0 + j] * xv[j];
-    }
-    Vsum[k] = acc;
-  }
-  __syncthreads();
-  // vis_loss = sum(G)/dem, G[s,t] = 1 - V_s.V_t (s != t): d/dV_s = -2 (Vsum - V_s) / dem
-  const float coef = -2.f * (10.f * p.vis_lam * __ldg(p.gout)) / dem;
-  for (int s = warp; s < d.Ns; s += kBwdThreads / 32) {  // dots[s] = x_s . gu_s
-    const float* x = p.vis + (size_t)row[s] * d.D;
-    const float sc = simn[s] * inv[s];
-    float acc = 0.f;
-    for (int k0 = 0; k0 < d.D; k0 += 256) {
-      float xv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = k0 + lane + 32 * j;
-        xv[j] = k < d.D ? __ldg(x + k) : 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = k0 + lane + 32 * j;
-        if (k < d.D) acc = fmaf(xv[j], Vsum[k] - sc * xv[j], acc);
+          for (int j = 0; j < 20; ++j)
+            if (f0 + j < d.F) accv = fmaf(g[f0 + j], v[j], accv);
+        }
+        dst[k] = accv;
       }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) dots[s] = acc * simn[s] * coef;
-  }
-  __syncthreads();
-  for (int k = tid; k < d.D; k += kBwdThreads) {
-    for (int s0 = 0; s0 < d.Ns; s0 += 8) {
-      float xs[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xs[j] = __ldg(p.vis + (size_t)row[min(s0 + j, d.Ns - 1)] * d.D + k);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int s = s0 + j;
-        if (s >= d.Ns) break;
-        const float iv = inv[s];             // 1/(n+eps)
-        const float nrm = 1.f / iv - kEps;   // n
-        const float sc = simn[s] * iv;
-        // dL/dx = gu/(n+eps) - x (x.gu) / (n (n+eps)^2);  gu = simn*coef*(Vsum - V_s)
-        const float c2 = nrm > 0.f ? dots[s] * iv * iv / nrm : 0.f;
-        const float gu = simn[s] * coef * (Vsum[k] - sc * xs[j]);
-        atomicAdd(p.gvis + (size_t)row[s] * d.D + k, gu * iv - xs[j] * c2);
+  } else {
+    // ------------------------------------------------ clustering-loss gradient ----
+    const int c = bid - d.F - d.NQ, a = c / d.Ne, e = c % d.Ne;
+    const float dem = __ldg(w.scal + 1);
+    if (e < __ldg(p.lens + a) && dem > 0.f) {
+      float* rows = sm;                       // [Ns][D] the picked rows of this entity
+      float* Vsum = rows + (size_t)d.Ns * d.D;
+      float* simn = Vsum + d.D;
+      float* inv = simn + d.Ns;
+      float* dots = inv + d.Ns;
+      int* row = reinterpret_cast<int*>(dots + d.Ns);
+      for (int s = tid; s < d.Ns; s += kBwdThreads) {
+        simn[s] = __ldg(p.D_sim + (size_t)(a * d.Ns + s) * d.NQ + c);
+        row[s] = (int)__ldg(p.D_ind + (size_t)(a * d.Ns + s) * d.NQ + c);
+      }
+      if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+      }
+      __syncthreads();
+      if (tid == 0) {  // one 1-D bulk copy per picked row (rows differ per frame)
+        mbar_arrive_expect_tx(&s_bar, (uint32_t)d.Ns * d.D * 4u);
+        for (int s = 0; s < d.Ns; ++s)
+          bulk_g2s(rows + (size_t)s * d.D, p.vis + (size_t)row[s] * d.D, (uint32_t)d.D * 4u, &s_bar);
+      }
+      float mn = INFINITY, mx = -INFINITY;
+      for (int s = 0; s < d.Ns; ++s) {
+        mn = fminf(mn, simn[s]);
+        mx = fmaxf(mx, simn[s]);
+      }
+      const float iden = 1.f / ((mx - mn) + kEps);
+      __syncthreads();
+      for (int s = tid; s < d.Ns; s += kBwdThreads) simn[s] = (simn[s] - mn) * iden;
+      mbar_wait(&s_bar, 0);
+      for (int s = warp; s < d.Ns; s += kBwdThreads / 32) {
+        const float* x = rows + (size_t)s * d.D;
+        float a0 = 0.f, a1 = 0.f;
+        for (int k = lane; k < d.D; k += 64) {
+          const float v0 = x[k], v1 = k + 32 < d.D ? x[k + 32] : 0.f;
+          a0 = fmaf(v0, v0, a0);
+          a1 = fmaf(v1, v1, a1);
+        }
+        const float acc = warp_sum(a0 + a1);
+        if (lane == 0) inv[s] = 1.f / (sqrtf(acc) + kEps);
+      }
+      __syncthreads();
+      for (int k = tid; k < d.D; k += kBwdThreads) {
+        float acc = 0.f;
+        for (int s = 0; s < d.Ns; ++s) acc = fmaf(simn[s] * inv[s], rows[(size_t)s * d.D + k], acc);
+        Vsum[k] = acc;
+      }
+      __syncthreads();
+      // vis_loss = sum(G)/dem, G[s,t] = 1 - V_s.V_t (s != t): d/dV_s = -2 (Vsum - V_s) / dem
+      const float coef = -2.f * (10.f * p.vis_lam * gout) / dem;
+      for (int s = warp; s < d.Ns; s += kBwdThreads / 32) {  // dots[s] = x_s . gu_s
+        const float* x = rows + (size_t)s * d.D;
+        const float sc = simn[s] * inv[s];
+        float a0 = 0.f, a1 = 0.f;
+        for (int k = lane; k < d.D; k += 64) {
+          const float v0 = x[k];
+          a0 = fmaf(v0, Vsum[k] - sc * v0, a0);
+          if (k + 32 < d.D) {
+            const float v1 = x[k + 32];
+            a1 = fmaf(v1, Vsum[k + 32] - sc * v1, a1);
+          }
+        }
+        const float acc = warp_sum(a0 + a1);
+        if (lane == 0) dots[s] = acc * simn[s] * coef;
+      }
+      __syncthreads();
+      if (tid == 0)
+        while (ld_acquire(flag) == 0) {
+        }
+      __syncthreads();
+      for (int k = tid; k < d.D; k += kBwdThreads) {
+        for (int s = 0; s < d.Ns; ++s) {
+          const float iv = inv[s];             // 1/(n+eps)
+          const float nrm = 1.f / iv - kEps;   // n
+          const float sc = simn[s] * iv;
+          // dL/dx = gu/(n+eps) - x (x.gu) / (n (n+eps)^2);  gu = simn*coef*(Vsum - V_s)
+          const float c2 = nrm > 0.f ? dots[s] * iv * iv / nrm : 0.f;
+          const float xv = rows[(size_t)s * d.D + k];
+          const float gu = simn[s] * coef * (Vsum[k] - sc * xv);
+          atomicAdd(p.gvis + (size_t)row[s] * d.D + k, gu * iv - xv * c2);
+        }
       }
     }
+  }
+  // last CTA out resets the scratch words for the next launch
+  __syncthreads();
+  if (tid == 0) s_ticket = ticket_acq_rel(finished);
+  __syncthreads();
+  if (s_ticket == (int)gridDim.x - 1 && tid == 0) {
+    *flag = 0;
+    *finished = 0;
   }
 }
 
@@ -1080,25 +1110,24 @@ NAFAE_API int nafae_ground_backward(const float* grad_margin_loss, const float* 
   p.d = d;
   p.vis_lam = vis_lam;
   p.train = train ? 1 : 0;
-  size_t smem = ((size_t)2 * d.Ns * d.NQ + (size_t)d.Ns * d.Na + 2 * (size_t)d.NQ +
-                 (size_t)kRowTile * d.D + 4) * 4;
+  // shared memory: the largest of the three CTA roles
+  size_t smem = ((size_t)d.Ns * d.NQ + (size_t)d.Ns * d.Na + 3 * (size_t)d.NQ + (size_t)kRowTile * d.D + 4) * 4;
   const size_t smem_w = (size_t)4 * d.F * 4;
+  const size_t smem_c = ((size_t)d.Ns * d.D + (size_t)d.D + 4 * (size_t)d.Ns) * 4;
   if (smem_w > smem) smem = smem_w;
+  if (p.train && smem_c > smem) smem = smem_c;
   NAFAE_REQUIRE(smem <= 200 * 1024, "ground backward: sizes need too much shared memory");
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ground_bwd_main_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ground_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
     if (e != cudaSuccess) {
       set_error("ground: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return -(int)e;
     }
   }
-  ground_bwd_main_kernel<<<d.F + d.NQ, kBwdThreads, smem, stream>>>(p);
-  int st = launch_status("ground_bwd_main_kernel");
-  if (st != 1 || !p.train) return st;
-  const size_t smem_c = ((size_t)d.D + 4 * d.Ns) * 4;
-  ground_bwd_cluster_kernel<<<d.NQ, kBwdThreads, smem_c, stream>>>(p);
-  return launch_status("ground_bwd_cluster_kernel");
+  const int grid = d.F + d.NQ + (p.train ? d.NQ : 0);
+  ground_bwd_kernel<<<grid, kBwdThreads, smem, stream>>>(p);
+  return launch_status("ground_bwd_kernel");
 }
 
 NAFAE_API int nafae_ground_postprocess(const int64_t* D_ind, const float* D_sim, int Na, int Ns,

@@ -14,7 +14,7 @@ from . import _C
 
 
 class GroundingStep(object):
-    KERNELS_PER_STEP_TRAIN = 5  # proposal_tail, align_pool_fwd_slab, ground_fwd, bwd_cluster, bwd_main
+    KERNELS_PER_STEP_TRAIN = 4  # proposal_tail, align_pool_fwd_slab, ground_fwd, ground_bwd
     KERNELS_PER_STEP_EVAL = 3
 
     def __init__(self, Na, Ns, Nb, Ne, D, C, H, W, n_props, pre_nms_topn=6000, nms_thresh=0.7,
@@ -70,21 +70,31 @@ class GroundingStep(object):
                     self.lens))
 
     # -- the step --------------------------------------------------------------------------
-    def run_detector(self):
-        """Detector-side half: proposal tail (batched NMS + top-N + padding) -> RoIAlignAvg 7x7.
-        Frozen in NAFAE (model.py:651,673,706-707): independent of the trainable weights, so it may
-        run ahead of / concurrently with the previous batch's head (see `capture_pipelined`)."""
-        Na, Ns, Nb, Ne, D = self.dims
+    def run_tail(self):
+        """Proposal tail: batched NMS + top-N + zero padding -> rois, roi_scores."""
+        Nb = self.dims[2]
         L, P = _C.lib, _C.ptr
-        s = _C.stream(self.dev)
         with torch.cuda.device(self.dev):
             _C.check(L.nafae_proposal_tail(P(self.proposals), P(self.scores), self.F, self.n,
                                            self.pre, Nb, self.thresh, P(self.rois),
-                                           P(self.roi_scores), None, s), "nafae_proposal_tail")
+                                           P(self.roi_scores), None, _C.stream(self.dev)),
+                     "nafae_proposal_tail")
+
+    def run_align(self):
+        """RoIAlignAvg 7x7 of the current rois -> pooled (R, C, 7, 7)."""
+        L, P = _C.lib, _C.ptr
+        with torch.cuda.device(self.dev):
             _C.check(L.nafae_roi_align_forward(P(self.features), self.scale, self.F, self.R, self.H,
                                                self.W, self.C, 7, 7, _C.POOL_AVG, P(self.rois),
-                                               P(self.pooled), 0, None, 0, s),
+                                               P(self.pooled), 0, None, 0, _C.stream(self.dev)),
                      "nafae_roi_align_forward")
+
+    def run_detector(self):
+        """Detector-side half: proposal tail -> RoIAlignAvg.  Frozen in NAFAE (model.py:651,673,
+        706-707): independent of the trainable weights, so it may run ahead of / concurrently with
+        earlier batches' head (see `capture_pipelined`)."""
+        self.run_tail()
+        self.run_align()
 
     def run_head(self, backward=None):
         """Head half: similarity + losses forward, then backward to dL/dvis_feats, dL/dword_feats.
@@ -130,33 +140,34 @@ class GroundingStep(object):
         self.graph.replay()
 
 
-def capture_pipelined(det_step, head_step, side_stream, extra_branch=None):
-    """CUDA graph of one software-pipelined training step:
+def capture_pipelined(align_step, next_step, streams, extra_branch=None):
+    """CUDA graph of one software-pipelined training step (three concurrent branches):
 
-        branch A (capturing stream): detector half of `det_step`   (batch k+1: NMS tail, RoIAlign)
-        branch B (side stream)     : head half of `head_step`      (batch k: DVSA fwd + bwd)
-        branch C (optional)        : `extra_branch()` on its own stream (e.g. gradient all-reduce)
+        A (capturing stream): RoIAlign of `align_step`        -- batch k+1, rois from the last replay
+        B (streams[0])      : proposal tail of `next_step`    -- batch k+2, rois for the next replay
+        C (streams[1])      : head (DVSA fwd + bwd) of `next_step` -- batch k
+        D (optional)        : `extra_branch(cur)` on its own stream (gradient all-reduce)
 
-    The detector is frozen in NAFAE, so batch k+1's detector half does not depend on batch k's
-    weight update: the two halves of consecutive batches overlap, like a data loader prefetch.
-    Every replay still executes one full detector half and one full head half; dependencies inside
-    a batch (tail -> RoIAlign, fwd -> bwd) and across replays (graphs serialise) are preserved.
-    Leave a few SMs to branch B/C with `nafae_set_reserved_sms` (the slab kernel is persistent)."""
-    det_step.run_detector()
-    head_step.run_head()
-    torch.cuda.synchronize(det_step.dev)
+    The detector is frozen in NAFAE, so a later batch's NMS / RoIAlign do not depend on an earlier
+    batch's weight update: the stages of consecutive batches overlap like a data-loader prefetch.
+    Every replay executes exactly one proposal tail, one RoIAlign and one head; dependencies inside
+    a batch (tail -> RoIAlign through `rois`, fwd -> bwd) are preserved because graphs serialise
+    and the two buffer sets alternate.  The slab kernel is persistent: leave a few SMs to the head
+    kernels with `nafae_set_reserved_sms` (the tail's small CTAs co-reside with it)."""
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         cur = torch.cuda.current_stream()
-        side_stream.wait_stream(cur)
-        streams = [side_stream]
-        with torch.cuda.stream(side_stream):
-            head_step.run_head()
+        joined = []
+        for st, fn in ((streams[0], next_step.run_tail), (streams[1], next_step.run_head)):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                fn()
+            joined.append(st)
         if extra_branch is not None:
             extra_stream = extra_branch(cur)
             if extra_stream is not None:
-                streams.append(extra_stream)
-        det_step.run_detector()
-        for st in streams:
+                joined.append(extra_stream)
+        align_step.run_align()
+        for st in joined:
             cur.wait_stream(st)
     return g
