@@ -642,27 +642,29 @@ __device__ void phase3_final(const FwdParams& p, const Ws& w) {
   __syncthreads();
   TRACE(121);
   // frame_score[a,s] = mean_o relu(Sf[o,s,a] - d[a,s] + Delta) + mean_o relu(Sf[a,s,o] - d[a,s] + Delta)
-  // summed over (a,s) this is sum over elements (p,s,q) of relu(x - d[q,s] + D) + relu(x - d[p,s] + D)
+  // Thread per (pp, s): its row Sf[pp,s,:] holds the "text o as a negative for video pp" hinges and
+  // column pp of frame slot s the "video o as a negative for text pp" hinges; both use d[pp,s].
   float part = 0.f;
   const float inv_na = 1.f / (float)d.Na;
   const float gscale = 10.f / (float)(d.Na * d.Ns) * inv_na;  // d(margin)/d(relu term)
-  for (int i = tid; i < n; i += kFwdThreads) {
-    const int q = i % d.Na, s = (i / d.Na) % d.Ns, pp = i / (d.Na * d.Ns);
-    const float x = Sf[i];
-    const float dq = Sf[(q * d.Ns + s) * d.Na + q], dp = Sf[(pp * d.Ns + s) * d.Na + pp];
-    const float vA = (x - dq) + p.Delta;  // video pp as a negative for text q
-    const float vB = (x - dp) + p.Delta;  // text q as a negative for video pp
-    part += fmaxf(vA, 0.f) + fmaxf(vB, 0.f);
-    float g = gscale * ((vA > 0.f ? 1.f : 0.f) + (vB > 0.f ? 1.f : 0.f));
-    if (pp == q) {  // d[q,s] enters every hinge of row/column q with a minus sign
-      int cnt = 0;
-      for (int o = 0; o < d.Na; ++o) {
-        cnt += ((Sf[(o * d.Ns + s) * d.Na + q] - dq) + p.Delta > 0.f) ? 1 : 0;
-        cnt += ((Sf[(q * d.Ns + s) * d.Na + o] - dq) + p.Delta > 0.f) ? 1 : 0;
-      }
-      g -= gscale * (float)cnt;
+  for (int i = tid; i < d.Na * d.Ns; i += kFwdThreads) {
+    const int pp = i / d.Ns, s = i - pp * d.Ns;
+    const float* row = Sf + (size_t)(pp * d.Ns + s) * d.Na;
+    const float dp = row[pp];
+    int cnt = 0;  // active hinges that contain -d[pp,s]
+    for (int o = 0; o < d.Na; ++o) {
+      const float x = row[o];
+      const float vB = (x - dp) + p.Delta;                                       // text o vs video pp
+      const float vA = (x - Sf[(size_t)(o * d.Ns + s) * d.Na + o]) + p.Delta;    // video pp vs text o
+      const float vC = (Sf[(size_t)(o * d.Ns + s) * d.Na + pp] - dp) + p.Delta;  // video o vs text pp
+      part += fmaxf(vB, 0.f) + fmaxf(vC, 0.f);
+      cnt += (vB > 0.f ? 1 : 0) + (vC > 0.f ? 1 : 0);
+      if (o != pp)
+        w.hgrad[(size_t)(pp * d.Ns + s) * d.Na + o] =
+            gscale * ((vA > 0.f ? 1.f : 0.f) + (vB > 0.f ? 1.f : 0.f));
     }
-    w.hgrad[i] = g;
+    // diagonal element: its own two hinges are relu(Delta) (+2 if Delta > 0) minus every active hinge
+    w.hgrad[(size_t)(pp * d.Ns + s) * d.Na + pp] = gscale * ((p.Delta > 0.f ? 2.f : 0.f) - (float)cnt);
   }
   part = warp_sum(part);
   if (lane == 0) s_part[warp] = part;
