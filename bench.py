@@ -44,6 +44,8 @@ def parse_args():
                     help="run the two halves of a step back to back instead of overlapping the head of "
                          "batch k with the detector half of batch k+1")
     ap.add_argument("--reserve-sms", type=int, default=-1)
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="use NCCL for the gradient all-reduce instead of the peer-memory kernel")
     return ap.parse_args()
 
 
@@ -219,7 +221,12 @@ def run_ours(args):
     # parameters; this path's dL/dword_feats is written straight into it
     buckets = None
     if world > 1:
-        buckets = [parallel.GradBucket(parallel.trainable_grad_elems(), dev, world) for _ in range(2)]
+        # symmetric (CUDA-IPC mapped) buckets + the two-shot NVLink all-reduce kernel (csrc/allreduce.cu);
+        # --nccl-allreduce falls back to torch.distributed's NCCL all-reduce on the same bucket size
+        if args.nccl_allreduce:
+            buckets = [parallel.GradBucket(parallel.trainable_grad_elems(), dev, world) for _ in range(2)]
+        else:
+            buckets = [parallel.PeerAllReduce(parallel.trainable_grad_elems(), dev) for _ in range(2)]
         for st, b in zip(steps, buckets):
             st.grad_word = b.views([(st.NQ, c["D"])])[0]
     from nafae_b200 import _C
@@ -233,9 +240,14 @@ def run_ours(args):
     for st, hb in zip(steps, host):
         st.load(hb)
         st.run()  # warm-up, produces valid state for the first pipelined replay
+    def allreduce(b):
+        if args.nccl_allreduce:
+            dist.all_reduce(b.buf, op=dist.ReduceOp.AVG)
+        else:
+            b.launch()
     if world > 1:
         for b in buckets:
-            dist.all_reduce(b.buf, op=dist.ReduceOp.AVG)  # communicator warm-up
+            allreduce(b)  # warm-up (communicator / kernel)
     torch.cuda.synchronize()
     graphs = []
     for j in range(2):
@@ -246,7 +258,7 @@ def run_ours(args):
                 return None
             comm.wait_stream(cur)
             with torch.cuda.stream(comm):
-                dist.all_reduce(buckets[j].buf, op=dist.ReduceOp.AVG)
+                allreduce(buckets[j])
             return comm
         if pipelined:
             graphs.append(capture_pipelined(steps[j], steps[1 - j], side, ar_branch))
@@ -270,8 +282,7 @@ def run_ours(args):
         for i in range(n):
             graphs[i & 1].replay()
         if buckets:  # flush: the last step's gradients are still un-reduced
-            buckets[(n - 1) & 1].allreduce_async()
-            buckets[(n - 1) & 1].wait()
+            allreduce(buckets[(n - 1) & 1])
 
     loop(Wm)
     barrier()
@@ -389,10 +400,15 @@ def run_ours(args):
         % (" || gradient all-reduce" if world > 1 else "", reserve)) if pipelined else (
         "sequential: one CUDA graph per step, five kernels back to back")
     if world > 1:
-        line["config"]["allreduce"] = ("NCCL all-reduce (AVG) per step over a flat fp32 bucket of %d elems, "
-                                       "captured as a parallel branch of the NEXT step's CUDA graph "
-                                       "(overlaps its NMS/RoIAlign); %d SMs left free for it"
-                                       % (parallel.trainable_grad_elems(), parallel.COMM_SMS))
+        line["config"]["allreduce"] = ("%s all-reduce (AVG) per step over a flat fp32 bucket of %d elems (%.1f MB), "
+                                       "a parallel branch of the NEXT step's CUDA graph (overlaps its "
+                                       "NMS/RoIAlign); %d SMs left free for it"
+                                       % ("NCCL" if args.nccl_allreduce else
+                                          "two-shot NVLink peer-memory kernel (allreduce_avg_kernel, %d CTAs)"
+                                          % buckets[0].num_ctas,
+                                          parallel.trainable_grad_elems(), parallel.trainable_grad_elems() * 4 / 1e6,
+                                          parallel.COMM_SMS))
+        line["gpu_launches"] = K * (steps[0].kernels_per_step() + (0 if args.nccl_allreduce else 1))
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

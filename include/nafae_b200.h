@@ -178,6 +178,27 @@ int nafae_ground_backward(const float* grad_margin_loss, const float* vis_feats,
 int nafae_ground_postprocess(const int64_t* D_ind, const float* D_sim, int Na, int Ns, int Nb,
                              int Ne, int64_t* out_ind, float* out_sim, cudaStream_t stream);
 
+/* ------------------------------------------------- data-parallel gradient all-reduce ---- */
+
+/* New functionality (the reference is single-GPU: --mGPUs is parsed and never read, model.py:91-99).
+ * Two-shot all-reduce (AVG) of a flat fp32 gradient bucket over NVLink peer memory, one process per
+ * GPU, world <= 8.  Each rank allocates a symmetric buffer with nafae_ar_alloc (cudaMalloc +
+ * cudaIpcGetMemHandle), exchanges the 64-byte handles out of band (torch.distributed / MPI), maps the
+ * peers' buffers with nafae_ar_open, and writes its gradients at byte offset nafae_ar_data_offset().
+ * nafae_allreduce_avg launches ONE kernel (no host state, graph-capturable) on `stream`; all ranks
+ * must launch it the same number of times with the same count / num_ctas.  Summation order is fixed
+ * (rank 0..world-1), so every replica holds bit-identical averages afterwards.
+ * bufs: host array of `world` device pointers as mapped in this process, bufs[rank] = own buffer.
+ * count_floats must be a multiple of 4*world (nafae_ar_buffer_bytes pads). */
+size_t nafae_ar_buffer_bytes(size_t count_floats, int world);
+size_t nafae_ar_data_offset(void);
+int nafae_ar_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int nafae_ar_open(const unsigned char* handle64, void** peer_ptr);
+int nafae_ar_close(void* peer_ptr);
+int nafae_ar_free(void* dev_ptr);
+int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t count_floats, int num_ctas,
+                        cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,13 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nafae_ground_postprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_void_p]),
+    "nafae_ar_buffer_bytes": (c_size_t, [c_size_t, c_int]),
+    "nafae_ar_data_offset": (c_size_t, []),
+    "nafae_ar_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), c_void_p]),
+    "nafae_ar_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "nafae_ar_close": (c_int, [c_void_p]),
+    "nafae_ar_free": (c_int, [c_void_p]),
+    "nafae_allreduce_avg": (c_int, [c_void_p, c_int, c_int, c_size_t, c_int, c_void_p]),
 }
 
 MISSING = []

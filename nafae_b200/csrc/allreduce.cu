@@ -1,0 +1,257 @@
+// Gradient all-reduce (AVG) over NVLink 5 / NVSwitch peer memory for the data-parallel step.
+//
+// The reference is single-GPU ("--mGPUs parsed, never read"); data parallelism
+// is new functionality and its only collective is the per-step all-reduce of the flat fp32 bucket of
+// trainable gradients (8.8 MB).  At ~60 us per step an NCCL all-reduce (58 us alone with 32 channels,
+// ~140 us when it shares the GPU with the HBM-bound RoIAlign kernel) is the critical path, so the
+// bucket lives in a symmetric buffer that every rank maps through CUDA IPC and ONE kernel does a
+// two-shot all-reduce with plain peer loads:
+//
+//   barrier 0   every rank's bucket is complete (its producer ran earlier on the same stream)
+//   phase 1     rank r reduces slice r: reads it from all `world` buffers in rank order (so every
+//               element is summed in ONE fixed order: replicas end up bit-identical), scales by
+//               1/world, writes it back into its own buffer
+//   barrier 1   all slices reduced
+//   phase 2     every rank copies the other ranks' reduced slices into its own buffer
+//   barrier 2   nobody still reads my slice: the next step may overwrite the bucket
+//
+// CTA b of every rank handles chunk b of every slice and synchronises only with CTA b of the other
+// ranks through per-CTA flag words in peer memory (st.release.sys / ld.acquire.sys): no intra-GPU
+// grid barrier, and since CTAs are dispatched in index order on every rank the lowest unfinished
+// chunk is always resident everywhere (no deadlock even when few SMs are free).  CTAs are small
+// (256 threads, <= 64 registers, no shared memory): four fit on each SM the persistent RoIAlign kernel
+// leaves free (nafae_set_reserved_sms).
+// The kernel has no host-side state (the epoch lives in the buffer): it is CUDA-graph capturable.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace nafae {
+namespace {
+
+constexpr int kArThreads = 256;
+constexpr int kArMaxWorld = 8;
+constexpr int kArMaxCtas = 256;
+// header layout (bytes) at the start of every rank's symmetric buffer
+constexpr size_t kArFlagsBytes = (size_t)3 * kArMaxCtas * kArMaxWorld * sizeof(unsigned);  // [stage][cta][rank]
+constexpr size_t kArHeaderBytes = kArFlagsBytes + 256;  // + epoch word, finish ticket
+
+struct ArParams {
+  char* bufs[kArMaxWorld];  // every rank's buffer base (own one included), as mapped in THIS process
+  int rank, world;
+  long long count;  // floats
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Plain (weak) 128-bit load.  Peer data is only read after this thread has passed a barrier whose
+// flag loads are acquire.sys (causality orders it after the peers' writes); no address is read
+// twice in one launch and L1 is invalidated at launch, so a stale line cannot be hit.
+__device__ __forceinline__ float4 ld_peer(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
+__device__ __forceinline__ unsigned* flag_ptr(char* base, int stage, int cta, int rank) {
+  return reinterpret_cast<unsigned*>(base) + ((size_t)stage * kArMaxCtas + cta) * kArMaxWorld + rank;
+}
+
+// CTA-level barrier with the same CTA index on every rank
+__device__ __forceinline__ void cta_barrier_all_ranks(const ArParams& p, int stage, unsigned epoch) {
+  // every thread's data writes happen-before the barrier; the release.sys stores below are
+  // cumulative over it, so no per-thread system fence is needed
+  __syncthreads();
+  const int tid = threadIdx.x;
+  if (tid < p.world) st_release_sys(flag_ptr(p.bufs[tid], stage, blockIdx.x, p.rank), epoch);
+  if (tid < p.world) {
+    const unsigned* f = flag_ptr(p.bufs[p.rank], stage, blockIdx.x, tid);
+    while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+    }
+  }
+  __syncthreads();
+}
+
+// W = compile-time bound on the world size (buffers beyond p.world are skipped), U = unroll
+template <int W, int U>
+__device__ __forceinline__ void reduce_slice(const ArParams& p, long long base, long long c_begin,
+                                             long long c_end, float scale, float4* out) {
+  const int tid = threadIdx.x;
+  for (long long i0 = c_begin; i0 < c_end; i0 += (long long)U * kArThreads) {
+    float4 v[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * kArThreads + tid;
+#pragma unroll
+      for (int r = 0; r < W; ++r)
+        if (r < p.world && i < c_end)
+          v[u][r] = ld_peer(reinterpret_cast<const float4*>(p.bufs[r] + kArHeaderBytes) + base + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * kArThreads + tid;
+      if (i < c_end) {
+        float4 acc = v[u][0];
+#pragma unroll
+        for (int r = 1; r < W; ++r)
+          if (r < p.world) {
+            acc.x += v[u][r].x;
+            acc.y += v[u][r].y;
+            acc.z += v[u][r].z;
+            acc.w += v[u][r].w;
+          }
+        acc.x *= scale;
+        acc.y *= scale;
+        acc.z *= scale;
+        acc.w *= scale;
+        out[i] = acc;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kArThreads, 4) allreduce_avg_kernel(const ArParams p) {
+  char* mine = p.bufs[p.rank];
+  unsigned* epoch_word = reinterpret_cast<unsigned*>(mine + kArFlagsBytes);
+  int* finished = reinterpret_cast<int*>(mine + kArFlagsBytes + 64);
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(epoch_word) + 1u;
+  const int tid = threadIdx.x;
+  const long long n4 = p.count >> 2;  // float4 elements (count is padded to a multiple of 4*world)
+  const long long slice4 = n4 / p.world;
+  const long long per_cta = (slice4 + gridDim.x - 1) / gridDim.x;
+  const long long c_begin = min(slice4, (long long)blockIdx.x * per_cta);
+  const long long c_end = min(slice4, c_begin + per_cta);
+  const float scale = 1.f / (float)p.world;
+
+  cta_barrier_all_ranks(p, 0, epoch);
+
+  // phase 1: reduce my slice (fixed rank order => identical bits on every replica).
+  // ~8 x 16 B peer loads in flight per thread whatever the world size (peer latency ~2-3 us).
+  {
+    const long long base = (long long)p.rank * slice4;
+    float4* out = reinterpret_cast<float4*>(mine + kArHeaderBytes) + base;
+    if (p.world == 2)
+      reduce_slice<2, 4>(p, base, c_begin, c_end, scale, out);
+    else if (p.world <= 4)
+      reduce_slice<4, 2>(p, base, c_begin, c_end, scale, out);
+    else
+      reduce_slice<8, 1>(p, base, c_begin, c_end, scale, out);
+  }
+
+  cta_barrier_all_ranks(p, 1, epoch);
+
+  // phase 2: gather the other ranks' reduced slices
+  for (int q = 1; q < p.world; ++q) {
+    const int r = (p.rank + q) % p.world;  // start at different peers to spread the links
+    const long long base = (long long)r * slice4;
+    const float4* src = reinterpret_cast<const float4*>(p.bufs[r] + kArHeaderBytes) + base;
+    float4* dst = reinterpret_cast<float4*>(mine + kArHeaderBytes) + base;
+    for (long long i0 = c_begin; i0 < c_end; i0 += 8 * kArThreads) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long i = i0 + u * kArThreads + tid;
+        if (i < c_end) v[u] = ld_peer(src + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long i = i0 + u * kArThreads + tid;
+        if (i < c_end) dst[i] = v[u];
+      }
+    }
+  }
+
+  cta_barrier_all_ranks(p, 2, epoch);
+
+  // the last CTA of this rank publishes the new epoch for the next launch
+  __shared__ int s_ticket;
+  if (tid == 0) s_ticket = atomicAdd(finished, 1);
+  __syncthreads();
+  if (s_ticket == (int)gridDim.x - 1 && tid == 0) {
+    *finished = 0;
+    *epoch_word = epoch;
+  }
+}
+
+}  // namespace
+}  // namespace nafae
+
+using namespace nafae;
+
+NAFAE_API size_t nafae_ar_buffer_bytes(size_t count_floats, int world) {
+  if (world < 1) world = 1;
+  const size_t pad = (size_t)4 * world;
+  const size_t padded = (count_floats + pad - 1) / pad * pad;
+  return kArHeaderBytes + padded * sizeof(float);
+}
+
+NAFAE_API size_t nafae_ar_data_offset(void) { return kArHeaderBytes; }
+
+NAFAE_API int nafae_ar_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  NAFAE_REQUIRE(dev_ptr && handle64 && bytes >= kArHeaderBytes, "ar_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    set_error("ar_alloc: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return -(int)e;
+  }
+  cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    set_error("ar_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    cudaFree(p);
+    return -(int)e;
+  }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  cudaDeviceSynchronize();
+  return 1;
+}
+
+NAFAE_API int nafae_ar_open(const unsigned char* handle64, void** peer_ptr) {
+  NAFAE_REQUIRE(handle64 && peer_ptr, "ar_open: NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    set_error("ar_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    return -(int)e;
+  }
+  return 1;
+}
+
+NAFAE_API int nafae_ar_close(void* peer_ptr) {
+  return cudaIpcCloseMemHandle(peer_ptr) == cudaSuccess ? 1 : 0;
+}
+
+NAFAE_API int nafae_ar_free(void* dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? 1 : 0; }
+
+NAFAE_API int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t count_floats,
+                                  int num_ctas, cudaStream_t stream) {
+  NAFAE_REQUIRE(bufs && world >= 1 && world <= kArMaxWorld && rank >= 0 && rank < world,
+                "allreduce: bad rank/world (world <= %d)", kArMaxWorld);
+  NAFAE_REQUIRE(num_ctas >= 1 && num_ctas <= kArMaxCtas, "allreduce: num_ctas must be in [1, %d]",
+                kArMaxCtas);
+  NAFAE_REQUIRE(count_floats % ((size_t)4 * world) == 0,
+                "allreduce: count must be a multiple of 4*world (use nafae_ar_buffer_bytes)");
+  if (world == 1 || count_floats == 0) return 1;
+  ArParams p;
+  for (int r = 0; r < kArMaxWorld; ++r) p.bufs[r] = r < world ? static_cast<char*>(bufs[r]) : nullptr;
+  for (int r = 0; r < world; ++r) NAFAE_REQUIRE(p.bufs[r], "allreduce: NULL buffer for rank %d", r);
+  p.rank = rank;
+  p.world = world;
+  p.count = (long long)count_floats;
+  allreduce_avg_kernel<<<num_ctas, kArThreads, 0, stream>>>(p);
+  return launch_status("allreduce_avg_kernel");
+}

@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 
 
-COMM_SMS = int(os.environ.get("NAFAE_COMM_SMS", "8"))  # SMs left to the collective while the slab kernel runs
+COMM_SMS = int(os.environ.get("NAFAE_COMM_SMS", "16"))  # SMs left to the collective while the slab kernel runs
 
 
 def trainable_grad_elems(vis_fc_dim=4096, glove_dim=200, ebd_dim=512):
@@ -97,6 +97,91 @@ class GradBucket(object):
         if self._done is not None:
             torch.cuda.current_stream().wait_event(self._done)
             self._done = None
+
+
+class _RawCudaArray(object):
+    """Minimal __cuda_array_interface__ carrier so torch can view memory the C library owns."""
+
+    def __init__(self, ptr, numel):
+        self.__cuda_array_interface__ = dict(shape=(int(numel),), typestr="<f4", data=(int(ptr), False),
+                                             version=2)
+
+
+class PeerAllReduce(object):
+    """Flat fp32 gradient bucket in a symmetric (CUDA-IPC mapped) buffer + the two-shot NVLink
+    all-reduce kernel of csrc/allreduce.cu.  One process per GPU, single node, world <= 8.
+
+    `buf` is a torch view of this rank's bucket (write gradients into `views(...)` of it);
+    `launch()` enqueues ONE kernel on the current stream (graph-capturable, no NCCL involved);
+    every rank must call it the same number of times.  torch.distributed is only used once, to
+    exchange the 64-byte IPC handles."""
+
+    def __init__(self, numel, device, rank=None, world=None, num_ctas=None):
+        import ctypes
+        from . import _C
+        self._C, self._ct = _C, ctypes
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.dev = torch.device(device)
+        pad = 4 * self.world
+        self.count = (int(numel) + pad - 1) // pad * pad
+        self.numel = int(numel)
+        self.num_ctas = int(num_ctas if num_ctas is not None else os.environ.get("NAFAE_AR_CTAS", "96"))
+        nbytes = int(_C.lib.nafae_ar_buffer_bytes(self.count, self.world))
+        own = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.dev):
+            _C.check(_C.lib.nafae_ar_alloc(nbytes, ctypes.byref(own), handle), "nafae_ar_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle))
+            self._ptrs = (ctypes.c_void_p * self.world)()
+            self._opened = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self._ptrs[r] = own.value
+                else:
+                    peer = ctypes.c_void_p()
+                    hb = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+                    _C.check(_C.lib.nafae_ar_open(hb, ctypes.byref(peer)), "nafae_ar_open")
+                    self._ptrs[r] = peer.value
+                    self._opened.append(peer.value)
+        self._own = own.value
+        off = int(_C.lib.nafae_ar_data_offset())
+        self.buf = torch.as_tensor(_RawCudaArray(self._own + off, self.count), device=self.dev)[: self.numel]
+        dist.barrier()
+
+    def views(self, shapes):
+        out, off = [], 0
+        for shp in shapes:
+            n = 1
+            for s in shp:
+                n *= int(s)
+            out.append(self.buf[off:off + n].view(*shp))
+            off += n
+        if off > self.buf.numel():
+            raise ValueError("bucket too small")
+        return out
+
+    def launch(self):
+        """All-reduce (AVG) the bucket in place on the current stream."""
+        if self.world <= 1:
+            return
+        with torch.cuda.device(self.dev):
+            st = self._C.lib.nafae_allreduce_avg(self._ptrs, self.rank, self.world, self.count,
+                                                 self.num_ctas, self._C.stream(self.dev))
+        self._C.check(st, "nafae_allreduce_avg")
+
+    def close(self):
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()
+        for p in self._opened:
+            self._C.lib.nafae_ar_close(self._ct.c_void_p(p))
+        self._opened = []
+        dist.barrier()
+        if self._own:
+            self.buf = None
+            self._C.lib.nafae_ar_free(self._ct.c_void_p(self._own))
+            self._own = None
 
 
 def capture_step_with_allreduce(step, reduce_bucket, side_stream):

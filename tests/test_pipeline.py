@@ -146,3 +146,28 @@ def test_cfg5_inference_sweep_sample_picks_and_boxes():
         want = odvsa.record_det(c["Nb"], ents, oD, oDs, ids, o_rois.reshape(-1, 5)[:, 1:])
         assert got[0] == want[0] and got[1] == want[1]
         np.testing.assert_array_equal(np.asarray(got[2]), np.asarray(want[2]))
+
+
+@gpu
+def test_symmetric_buffer_alloc_and_world1_allreduce_is_identity():
+    """The IPC-mapped gradient bucket: allocation, torch view, world-1 launch (multi-rank behaviour is
+    exercised by tools/test_allreduce.py under torchrun and by bench.py --gpus N)."""
+    import ctypes
+    from nafae_b200 import _C
+    from nafae_b200.parallel import _RawCudaArray
+    n = 4096
+    nbytes = int(_C.lib.nafae_ar_buffer_bytes(n, 1))
+    own = ctypes.c_void_p()
+    handle = (ctypes.c_ubyte * 64)()
+    assert _C.lib.nafae_ar_alloc(nbytes, ctypes.byref(own), handle) == 1
+    assert any(bytes(handle))
+    off = int(_C.lib.nafae_ar_data_offset())
+    buf = torch.as_tensor(_RawCudaArray(own.value + off, n), device="cuda:0")
+    assert float(buf.abs().sum()) == 0.0  # zero-filled
+    buf.copy_(torch.arange(n, dtype=torch.float32, device="cuda:0"))
+    ptrs = (ctypes.c_void_p * 1)(own.value)
+    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 1, n, 8, _C.stream()) == 1
+    torch.cuda.synchronize()
+    assert torch.equal(buf.cpu(), torch.arange(n, dtype=torch.float32))
+    del buf
+    assert _C.lib.nafae_ar_free(own) == 1
