@@ -156,18 +156,24 @@ def capture_pipelined(align_step, next_step, streams, extra_branch=None):
     kernels with `nafae_set_reserved_sms` (the tail's small CTAs co-reside with it)."""
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        cur = torch.cuda.current_stream()
-        joined = []
-        for st, fn in ((streams[0], next_step.run_tail), (streams[1], next_step.run_head)):
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                fn()
-            joined.append(st)
-        if extra_branch is not None:
-            extra_stream = extra_branch(cur)
-            if extra_stream is not None:
-                joined.append(extra_stream)
-        align_step.run_align()
-        for st in joined:
-            cur.wait_stream(st)
+        capture_pipelined_body(align_step, next_step, streams, extra_branch)
     return g
+
+
+def capture_pipelined_body(align_step, next_step, streams, extra_branch=None):
+    """The fork / join of one pipelined step on the capturing stream (call inside torch.cuda.graph;
+    several bodies in a row make a multi-step graph that amortises the graph-launch latency)."""
+    cur = torch.cuda.current_stream()
+    joined = []
+    for st, fn in ((streams[0], next_step.run_tail), (streams[1], next_step.run_head)):
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            fn()
+        joined.append(st)
+    if extra_branch is not None:
+        extra_stream = extra_branch(cur)
+        if extra_stream is not None:
+            joined.append(extra_stream)
+    align_step.run_align()
+    for st in joined:
+        cur.wait_stream(st)
