@@ -34,8 +34,8 @@ UNIT = "segments/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cfg", default="cfg2", choices=["cfg2", "cfg2_real", "cfg4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -139,7 +139,7 @@ class ClockSampler(object):
                 uuid = "GPU-" + uuid
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", uuid, "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -148,7 +148,7 @@ class ClockSampler(object):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -314,6 +314,10 @@ def run_ours(args):
     loop(Wm)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.1)  # let nvidia-smi start
+    loop(min(Wm, 20))  # all ranks: re-warm after the pause so the timed region starts at load clocks
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     loop(K)
@@ -362,7 +366,7 @@ def run_ours(args):
         free = [torch.cuda.Event() for _ in range(2)]
         for ev in free:
             ev.record()
-        Ke = max(10, min(K, 50))
+        Ke = max(10, min(K, 100))
         _C.lib.nafae_set_reserved_sms(0)
         e2e_graphs = [st.capture() for st in steps]
 

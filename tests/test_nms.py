@@ -202,3 +202,42 @@ def test_proposal_tail_equals_reference_python_loop():
         out_s[i, : keep.numel()] = st[i][keep]
     rois, rsc = proposal_tail(pt, st, 6000, post, 0.7)
     assert torch.equal(rois, out) and torch.equal(rsc, out_s)
+
+
+@gpu
+def test_proposal_layer_module_equals_reference_style_loop():
+    """`_ProposalLayer` mirror (anchors + decode + clip + sort + fused tail) vs the reference's own
+    per-frame loop (proposal_layer.py:130-163) run with this package's nms()."""
+    import types
+    from nafae_b200.model.nms.nms_wrapper import nms
+    from nafae_b200.model.rpn.proposal_layer import _ProposalLayer
+    from nafae_b200.model.rpn.bbox_transform import bbox_transform_inv, clip_boxes
+    cfg = types.SimpleNamespace(TEST=types.SimpleNamespace(RPN_PRE_NMS_TOP_N=6000, RPN_POST_NMS_TOP_N=20,
+                                                          RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=16))
+    layer = _ProposalLayer(16, [4, 8, 16, 32], [0.5, 1, 2], cfg)
+    torch.manual_seed(3)
+    B, A, H, W = 4, 12, 14, 14
+    cls = torch.rand(B, 2 * A, H, W, device=_dev())
+    deltas = torch.randn(B, 4 * A, H, W, device=_dev()) * 0.2
+    info = torch.tensor([[224., 224., 1.]] * B, device=_dev())
+    out = layer((cls, deltas, info, "TEST"))
+    assert out.shape == (B, 20, 5)
+    # reference-style loop on the same decoded boxes
+    scores = cls[:, A:].permute(0, 2, 3, 1).contiguous().view(B, -1)
+    sx = torch.arange(0, W, device=_dev(), dtype=torch.float32) * 16
+    sy = torch.arange(0, H, device=_dev(), dtype=torch.float32) * 16
+    yy, xx = torch.meshgrid(sy, sx, indexing="ij")
+    shifts = torch.stack((xx.reshape(-1), yy.reshape(-1), xx.reshape(-1), yy.reshape(-1)), 1)
+    anchors = (layer._anchors.to(_dev()).view(1, A, 4) + shifts.view(-1, 1, 4)).view(1, -1, 4).expand(B, -1, 4)
+    props = clip_boxes(bbox_transform_inv(anchors, deltas.permute(0, 2, 3, 1).contiguous().view(B, -1, 4), B),
+                       info, B)
+    _, order = torch.sort(scores, 1, True)
+    want = scores.new_zeros(B, 20, 5)
+    want_s = scores.new_zeros(B, 20)
+    for i in range(B):
+        p, s = props[i][order[i]], scores[i][order[i]].view(-1, 1)
+        keep = nms(torch.cat((p, s), 1), 0.7).long().view(-1)[:20]
+        want[i, :, 0] = i
+        want[i, : keep.numel(), 1:] = p[keep]
+        want_s[i, : keep.numel()] = s[keep, 0]
+    assert torch.equal(out, want) and torch.equal(layer.get_roi_score(), want_s)
