@@ -144,6 +144,33 @@ def test_slab_kernel_matches_oracle(name, F, C, H, W, per_frame, shuffle, pool):
 
 
 @gpu
+@pytest.mark.parametrize("name,F,C,H,W,per_frame,shuffle", [
+    ("cfg2_like", 6, 64, 38, 50, [20] * 6, False),
+    ("real_14x14", 5, 64, 14, 14, [20] * 5, False),
+    ("ragged_shuffled_empty_frame", 5, 32, 38, 50, [3, 0, 40, 1, 17], True),
+    ("chunked_300_in_one_frame", 3, 8, 38, 50, [300, 5, 130], True),
+    ("many_frames_few_channels", 40, 8, 14, 14, [4] * 40, False),
+    ("odd_map_generic_fallback", 2, 8, 37, 50, [9, 9], False),
+])
+def test_avg_backward_through_module_matches_oracle(name, F, C, H, W, per_frame, shuffle):
+    """RoIAlignAvg backward through the module at slab-kernel shapes (ragged / empty frames,
+    >table-size frames, fallback shapes): frames without RoIs must come back as exact zeros."""
+    _, RoIAlignAvg, _ = _mods()
+    rs = np.random.RandomState(abs(hash(name)) % 1000)
+    feat = synth.conv5_maps(rs, F, C, H, W)
+    rois = _frame_rois(rs, F, per_frame, H * 16, W * 16, shuffle)
+    gy = rs.randn(rois.shape[0], C, 7, 7).astype(np.float32)
+    f = _t(feat).requires_grad_(True)
+    junk = torch.full((F * C * H * W * 2,), float("nan"), device=_dev())  # poison the allocator
+    del junk
+    RoIAlignAvg(7, 7, 1 / 16.)(f, _t(rois)).backward(_t(gy))
+    ref = ocpu.roi_align_avg_backward(gy, feat, rois, 1 / 16.)
+    got = f.grad.cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=RTOL * np.abs(ref).max())
+
+
+@gpu
 def test_out_of_range_batch_index_rows_are_zero():
     _, RoIAlignAvg, _ = _mods()
     rs = np.random.RandomState(2)

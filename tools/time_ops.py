@@ -49,10 +49,21 @@ def main():
     mod = RoIAlignAvg(7, 7, 1 / 16., exact=a.exact)
     out_bytes = rois2.shape[0] * c["C"] * 49 * 4
     in_bytes = feat.numel() * 4
+    featg = feat.clone().requires_grad_(True)
+    outg = mod(featg, rois2)
+    gy = torch.randn_like(outg)
+
+    def bwd():
+        featg.grad = None
+        outg.backward(gy, retain_graph=True)
+    from nafae_b200.model.roi_pooling.modules.roi_pool import _RoIPooling
+    pool = _RoIPooling(7, 7, 1 / 16.)
     for name, fn, nbytes in (
         ("proposal_tail", lambda: proposal_tail(props, scores, c["pre"], c["Nb"], 0.7), None),
         ("nms_batched(full)", lambda: nms_batched(torch.cat((props, scores.unsqueeze(2)), 2), 0.7), None),
         ("roi_align_avg", lambda: mod(feat, rois2), in_bytes + out_bytes),
+        ("roi_align_avg bwd", bwd, in_bytes + out_bytes),
+        ("roi_pool fwd", lambda: pool(feat, rois2), in_bytes + out_bytes),
     ):
         med, mn = timeit(fn, flush=flush)
         extra = ""
