@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--steps-per-graph", type=int, default=1,
                     help="pipelined steps captured per CUDA graph (measured: 1 is fastest, 60.8 us/step vs "
                          "63.7 us with 16 -- join/fork inside a graph costs more than back-to-back replays)")
+    ap.add_argument("--no-gate", action="store_true",
+                    help="do not hold the all-reduce branch behind the RoIAlign kernel's residency gate")
+    ap.add_argument("--gate-head", action="store_true",
+                    help="also hold the head branch behind the gate (measured slower)")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="use NCCL for the gradient all-reduce instead of the peer-memory kernel")
     return ap.parse_args()
@@ -235,8 +239,10 @@ def run_ours(args):
     from nafae_b200 import _C
     from nafae_b200.pipeline import capture_pipelined, capture_pipelined_body
     pipelined = not args.no_pipeline
-    reserve = args.reserve_sms if args.reserve_sms >= 0 else (
-        (HEAD_SMS if pipelined else 0) + (parallel.COMM_SMS if world > 1 else 0))
+    comm_sms = 0
+    if world > 1 and (args.nccl_allreduce or buckets[0].cta_threads != 128 or not pipelined):
+        comm_sms = parallel.COMM_SMS  # the 128-thread all-reduce CTAs co-reside with the slab CTAs instead
+    reserve = args.reserve_sms if args.reserve_sms >= 0 else (HEAD_SMS if pipelined else 0) + comm_sms
     _C.lib.nafae_set_reserved_sms(reserve)
     side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
     comm = torch.cuda.Stream(dev) if world > 1 else None
@@ -261,10 +267,12 @@ def run_ours(args):
                 return None
             comm.wait_stream(cur)
             with torch.cuda.stream(comm):
+                if pipelined and not args.no_gate:
+                    steps[j].wait_gate(1)  # spread over the reserved SMs only (see nafae_gate_wait)
                 allreduce(buckets[j])
             return comm
         if pipelined:
-            graphs.append(capture_pipelined(steps[j], steps[1 - j], side, ar_branch))
+            graphs.append(capture_pipelined(steps[j], steps[1 - j], side, ar_branch, gate_head=args.gate_head))
         else:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -285,6 +293,8 @@ def run_ours(args):
                     return None
                 comm.wait_stream(cur)
                 with torch.cuda.stream(comm):
+                    if not args.no_gate:
+                        steps[j].wait_gate(1)
                     allreduce(buckets[j])
                 return comm
             return br
@@ -292,7 +302,7 @@ def run_ours(args):
         with torch.cuda.graph(big):
             for s_ in range(S):
                 j = s_ & 1
-                capture_pipelined_body(steps[j], steps[1 - j], side, ar_for(j))
+                capture_pipelined_body(steps[j], steps[1 - j], side, ar_for(j), gate_head=args.gate_head)
         torch.cuda.synchronize()
 
     def barrier():
@@ -331,10 +341,8 @@ def run_ours(args):
 
     # dominant kernel alone, same stream, same alternating inputs (roofline.achieved)
     def align_only(st):
-        _C.check(_C.lib.nafae_roi_align_forward(_C.ptr(st.features), st.scale, st.F, st.R, st.H, st.W,
-                                                st.C, 7, 7, _C.POOL_AVG, _C.ptr(st.rois),
-                                                _C.ptr(st.pooled), 0, None, 0, _C.stream(dev)),
-                 "nafae_roi_align_forward")
+        st.run_align()  # same call (workspace: work stealing) as inside the step graphs
+
     for i in range(Wm):
         align_only(steps[i & 1])
     torch.cuda.synchronize()
@@ -433,12 +441,13 @@ def run_ours(args):
     if world > 1:
         line["config"]["allreduce"] = ("%s all-reduce (AVG) per step over a flat fp32 bucket of %d elems (%.1f MB), "
                                        "a parallel branch of the NEXT step's CUDA graph (overlaps its "
-                                       "NMS/RoIAlign); %d SMs left free for it"
+                                       "NMS/RoIAlign, launched behind the RoIAlign kernel's residency gate); "
+                                       "%d SMs left free for it"
                                        % ("NCCL" if args.nccl_allreduce else
-                                          "two-shot NVLink peer-memory kernel (allreduce_avg_kernel, %d CTAs)"
-                                          % buckets[0].num_ctas,
+                                          "two-shot NVLink peer-memory kernel (allreduce_avg_kernel, %d CTAs x %d threads)"
+                                          % (buckets[0].num_ctas, buckets[0].cta_threads),
                                           parallel.trainable_grad_elems(), parallel.trainable_grad_elems() * 4 / 1e6,
-                                          parallel.COMM_SMS))
+                                          comm_sms))
         line["gpu_launches"] = K * (steps[0].kernels_per_step() + (0 if args.nccl_allreduce else 1))
     if e2e:
         line["e2e"] = e2e

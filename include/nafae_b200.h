@@ -52,6 +52,20 @@ const char* nafae_last_error(void);
  * previous value.  n is clamped to [0, SMs-1]. */
 int nafae_set_reserved_sms(int n);
 
+/* Residency gate for kernels that run CONCURRENTLY with the persistent RoIAlign kernel (the head
+ * of an earlier batch, the gradient all-reduce).  The block scheduler places CTAs breadth-first:
+ * a concurrent kernel launched at the same time lands on every SM and keeps the 210 KB-per-CTA
+ * persistent kernel off those SMs until its CTAs retire.  With a gate the persistent kernel bumps
+ * an epoch once ALL its CTAs are resident, and nafae_gate_wait enqueues a one-warp kernel (it
+ * co-resides with anything) that returns only then -- so whatever follows it on `stream` can only
+ * land on the SMs left free by nafae_set_reserved_sms.  `gate` = the workspace passed to
+ * nafae_roi_align_forward (its first NAFAE_GATE_BYTES); `slot` in [0, 6) identifies the waiting
+ * branch (one slot per concurrent stream).  The wait returns once the gate has been opened by a
+ * launch this slot has not yet seen. */
+#define NAFAE_GATE_BYTES 32
+#define NAFAE_ROI_ALIGN_WS_BYTES 64
+int nafae_gate_wait(void* gate, int slot, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------- NMS ---- */
 
 /* Replaces nms_cuda_compute() -- lib/model/nms/src/nms_cuda_kernel.h:5-6 (impl
@@ -109,7 +123,9 @@ int ROIAlignBackwardLaucher(const float* top_diff, const float spatial_scale, co
  * (R, C, h+1, w+1) intermediate.  out_height x out_width is the MODULE's aligned size (7x7 for
  * RoIAlignAvg(7, 7, 1/16)); with pool_mode != NONE the sampled grid is (out+1) x (out+1).
  * top_data (R, C, out_height, out_width) is fully written (no zero-fill needed).
- * workspace: nafae_roi_align_workspace_bytes(batch_size, num_rois) bytes (may be 0 -> NULL ok). */
+ * workspace: optional (NULL / 0 is fine).  NAFAE_ROI_ALIGN_WS_BYTES of device memory, ZERO-INITIALISED
+ * ONCE by the caller and then left to the library, private to one stream: the residency gate of
+ * nafae_gate_wait (below). */
 size_t nafae_roi_align_workspace_bytes(int batch_size, int num_rois);
 int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size,
                             int num_rois, int height, int width, int channels, int out_height,
@@ -189,7 +205,11 @@ int nafae_ground_postprocess(const int64_t* D_ind, const float* D_sim, int Na, i
  * must launch it the same number of times with the same count / num_ctas.  Summation order is fixed
  * (rank 0..world-1), so every replica holds bit-identical averages afterwards.
  * bufs: host array of `world` device pointers as mapped in this process, bufs[rank] = own buffer.
- * count_floats must be a multiple of 4*world (nafae_ar_buffer_bytes pads). */
+ * count_floats must be a multiple of 4*world (nafae_ar_buffer_bytes pads).
+ * cta_threads: 0 = bulk-copy kernel (cp.async.bulk pulls the slice from every rank into shared
+ * memory, reduces, and pushes the result into every rank's buffer; one CTA per SM, num_ctas = the SMs
+ * nafae_set_reserved_sms keeps free); 256 / 128 = per-thread 16-byte loads (four / eight CTAs per
+ * SM).  When it overlaps the RoIAlign kernel, enqueue nafae_gate_wait first (see there). */
 size_t nafae_ar_buffer_bytes(size_t count_floats, int world);
 size_t nafae_ar_data_offset(void);
 int nafae_ar_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
@@ -197,7 +217,7 @@ int nafae_ar_open(const unsigned char* handle64, void** peer_ptr);
 int nafae_ar_close(void* peer_ptr);
 int nafae_ar_free(void* dev_ptr);
 int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t count_floats, int num_ctas,
-                        cudaStream_t stream);
+                        int cta_threads, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

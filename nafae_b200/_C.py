@@ -26,6 +26,7 @@ SIGNATURES = {
     "nafae_abi_version": (c_int, []),
     "nafae_last_error": (ctypes.c_char_p, []),
     "nafae_set_reserved_sms": (c_int, [c_int]),
+    "nafae_gate_wait": (c_int, [c_void_p, c_int, c_void_p]),
     "nms_cuda_compute": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float]),
     "nafae_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nafae_nms_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
@@ -62,7 +63,7 @@ SIGNATURES = {
     "nafae_ar_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "nafae_ar_close": (c_int, [c_void_p]),
     "nafae_ar_free": (c_int, [c_void_p]),
-    "nafae_allreduce_avg": (c_int, [c_void_p, c_int, c_int, c_size_t, c_int, c_void_p]),
+    "nafae_allreduce_avg": (c_int, [c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_void_p]),
 }
 
 MISSING = []
@@ -77,6 +78,8 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 FLAG_EXACT = 1
+GATE_BYTES = 32
+ROI_ALIGN_WS_BYTES = 64
 
 
 class NafaeError(RuntimeError):

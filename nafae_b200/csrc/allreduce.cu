@@ -19,8 +19,12 @@
 // ranks through per-CTA flag words in peer memory (st.release.sys / ld.acquire.sys): no intra-GPU
 // grid barrier, and since CTAs are dispatched in index order on every rank the lowest unfinished
 // chunk is always resident everywhere (no deadlock even when few SMs are free).  CTAs are small
-// (256 threads, <= 64 registers, no shared memory): four fit on each SM the persistent RoIAlign kernel
-// leaves free (nafae_set_reserved_sms).
+// (no shared memory, <= 64 registers) and come in two sizes: 256 threads -- four fit on each SM the
+// persistent RoIAlign kernel leaves free (nafae_set_reserved_sms) -- and 128 threads, 8 K registers:
+// one of those fits BESIDE a resident RoIAlign CTA (544 threads x 96 registers leave 13 K), so the
+// collective needs no SMs of its own.  In both cases launch it behind the RoIAlign kernel's residency
+// gate (nafae_gate_wait): started at the same instant, its CTAs would land on every SM first and
+// keep the 210 KB persistent CTAs out until the whole all-reduce has finished.
 // The kernel has no host-side state (the epoch lives in the buffer): it is CUDA-graph capturable.
 #include <string.h>
 
@@ -29,7 +33,7 @@
 namespace nafae {
 namespace {
 
-constexpr int kArThreads = 256;
+constexpr int kArThreadsMax = 256;
 constexpr int kArMaxWorld = 8;
 constexpr int kArMaxCtas = 256;
 // header layout (bytes) at the start of every rank's symmetric buffer
@@ -82,7 +86,7 @@ __device__ __forceinline__ void cta_barrier_all_ranks(const ArParams& p, int sta
 }
 
 // W = compile-time bound on the world size (buffers beyond p.world are skipped), U = unroll
-template <int W, int U>
+template <int W, int U, int kArThreads>
 __device__ __forceinline__ void reduce_slice(const ArParams& p, long long base, long long c_begin,
                                              long long c_end, float scale, float4* out) {
   const int tid = threadIdx.x;
@@ -119,7 +123,9 @@ __device__ __forceinline__ void reduce_slice(const ArParams& p, long long base, 
   }
 }
 
-__global__ void __launch_bounds__(kArThreads, 4) allreduce_avg_kernel(const ArParams p) {
+template <int kArThreads>
+__global__ void __launch_bounds__(kArThreads, 1024 / kArThreads) allreduce_avg_kernel(const ArParams p) {
+  NAFAE_CTA_TRACE(cta_trace, 5);
   char* mine = p.bufs[p.rank];
   unsigned* epoch_word = reinterpret_cast<unsigned*>(mine + kArFlagsBytes);
   int* finished = reinterpret_cast<int*>(mine + kArFlagsBytes + 64);
@@ -140,11 +146,11 @@ __global__ void __launch_bounds__(kArThreads, 4) allreduce_avg_kernel(const ArPa
     const long long base = (long long)p.rank * slice4;
     float4* out = reinterpret_cast<float4*>(mine + kArHeaderBytes) + base;
     if (p.world == 2)
-      reduce_slice<2, 4>(p, base, c_begin, c_end, scale, out);
+      reduce_slice<2, 4, kArThreads>(p, base, c_begin, c_end, scale, out);
     else if (p.world <= 4)
-      reduce_slice<4, 2>(p, base, c_begin, c_end, scale, out);
+      reduce_slice<4, 2, kArThreads>(p, base, c_begin, c_end, scale, out);
     else
-      reduce_slice<8, 1>(p, base, c_begin, c_end, scale, out);
+      reduce_slice<8, 1, kArThreads>(p, base, c_begin, c_end, scale, out);
   }
 
   cta_barrier_all_ranks(p, 1, epoch);
@@ -182,10 +188,170 @@ __global__ void __launch_bounds__(kArThreads, 4) allreduce_avg_kernel(const ArPa
   }
 }
 
+
+// ------------------------------------------------------------- bulk-copy (TMA) variant ----
+// Same two-shot data flow, fused into ONE pass and driven by the bulk-copy engine instead of
+// per-thread 16-byte loads:
+//   barrier 0   every rank's bucket is complete
+//   per chunk   cp.async.bulk the chunk of my slice from all `world` buffers into shared memory
+//               (peer buffers over NVLink), add them in rank order, scale, and cp.async.bulk the
+//               result from shared memory into EVERY rank's buffer (the all-gather is a push)
+//   barrier 2   all pushes into my buffer have landed / nobody still reads my input
+// A pull with plain loads needs (NVLink bandwidth x ~3 us latency) ~ 2 MB of loads in flight, i.e.
+// registers and LSU slots of ~100 SMs; here ONE thread per CTA keeps ~90 KB of peer data in flight
+// per SM (4-slot ring, the own copy goes through registers), so the few SMs left to the collective
+// carry the traffic, one phase and one cross-GPU barrier disappear, and there is no gather pass
+// re-reading the reduced slices.
+constexpr int kTmaThreads = 256;
+constexpr int kTmaStages = 4;             // chunks in the peer-data ring: three in flight per CTA
+constexpr int kTmaRingBytes = 128 * 1024;
+
+template <int W>
+struct TmaCfg {  // W = compile-time bound on the world size
+  // per peer per stage, a multiple of 4 KB (16 bytes per thread per pass of the 256 threads)
+  static constexpr int kChunkBytes = kTmaRingBytes / (kTmaStages * (W - 1)) / 4096 * 4096;
+  static constexpr int kChunk4 = kChunkBytes / 16;
+  static constexpr int kOwn = kChunk4 / kTmaThreads;  // float4 of the own copy per thread
+  static constexpr size_t kRing = (size_t)kTmaStages * (W - 1) * kChunkBytes;
+  static constexpr size_t kSmem = kRing + 2 * (size_t)kChunkBytes;
+};
+
+template <int W>
+__global__ void __launch_bounds__(kTmaThreads, 1) allreduce_tma_kernel(const ArParams p) {
+  NAFAE_CTA_TRACE(cta_trace, 5);
+  constexpr int kChunk4 = TmaCfg<W>::kChunk4;
+  constexpr int kOwn = TmaCfg<W>::kOwn;
+  extern __shared__ __align__(128) unsigned char ar_smem[];
+  float4* in = reinterpret_cast<float4*>(ar_smem);                          // [stage][W-1][kChunk4]
+  float4* out = reinterpret_cast<float4*>(ar_smem + TmaCfg<W>::kRing);      // [2][kChunk4]
+  __shared__ __align__(8) uint64_t full[kTmaStages];
+
+  char* mine = p.bufs[p.rank];
+  unsigned* epoch_word = reinterpret_cast<unsigned*>(mine + kArFlagsBytes);
+  int* finished = reinterpret_cast<int*>(mine + kArFlagsBytes + 64);
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(epoch_word) + 1u;
+  const int tid = threadIdx.x;
+  const long long n4 = p.count >> 2;
+  const long long slice4 = n4 / p.world;
+  const long long per_cta = (slice4 + gridDim.x - 1) / gridDim.x;
+  const long long c_begin = min(slice4, (long long)blockIdx.x * per_cta);
+  const long long c_end = min(slice4, c_begin + per_cta);
+  const long long base4 = (long long)p.rank * slice4;  // my slice inside every buffer
+  const float scale = 1.f / (float)p.world;
+  const int nchunks = (int)((c_end - c_begin + kChunk4 - 1) / kChunk4);
+  const float4* own = reinterpret_cast<const float4*>(mine + kArHeaderBytes) + base4 + c_begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  cta_barrier_all_ranks(p, 0, epoch);  // includes __syncthreads on both sides
+
+  auto chunk_len4 = [&](int i) { return (int)min((long long)kChunk4, c_end - (c_begin + (long long)i * kChunk4)); };
+  auto issue_loads = [&](int i) {  // thread 0: the peers' copies of chunk i -> ring slot i % stages
+    const int s = i % kTmaStages;
+    const uint32_t bytes = (uint32_t)chunk_len4(i) * 16u;
+    const long long off4 = base4 + c_begin + (long long)i * kChunk4;
+    mbar_arrive_expect_tx(&full[s], bytes * (uint32_t)(p.world - 1));
+    for (int q = 1; q < p.world; ++q) {
+      const int r = (p.rank + q) % p.world;  // start at different peers to spread the links
+      const int slot = r < p.rank ? r : r - 1;
+      bulk_g2s(in + ((size_t)s * (W - 1) + slot) * kChunk4,
+               reinterpret_cast<const float4*>(p.bufs[r] + kArHeaderBytes) + off4, bytes, &full[s]);
+    }
+  };
+  if (tid == 0) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    for (int i = 0; i < kTmaStages - 1 && i < nchunks; ++i) issue_loads(i);
+  }
+  for (int i = 0; i < nchunks; ++i) {
+    const int s = i % kTmaStages, so = i & 1;
+    const int len4 = chunk_len4(i);
+    // slot of chunk i-1 is free since the closing __syncthreads of the previous iteration
+    if (tid == 0 && i + kTmaStages - 1 < nchunks) issue_loads(i + kTmaStages - 1);
+    // own copy -> registers, in flight while the peers' data arrives
+    float4 mine4[kOwn];
+#pragma unroll
+    for (int j = 0; j < kOwn; ++j) {
+      const int k = tid + j * kTmaThreads;
+      mine4[j] = k < len4 ? own[(size_t)i * kChunk4 + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    mbar_wait(&full[s], (uint32_t)(i / kTmaStages) & 1u);
+    // the bulk stores that read out[so] two chunks ago must have drained it
+    if (tid == 0 && i >= 2) bulk_wait_read<1>();
+    __syncthreads();
+    const float4* src = in + (size_t)s * (W - 1) * kChunk4;
+    float4* dst = out + (size_t)so * kChunk4;
+#pragma unroll
+    for (int j = 0; j < kOwn; ++j) {
+      const int k = tid + j * kTmaThreads;
+      if (k < len4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < W; ++r)  // rank order; only the slice owner adds: replicas get its bits
+          if (r < p.world) {
+            const float4 v = r == p.rank ? mine4[j] : src[(size_t)(r < p.rank ? r : r - 1) * kChunk4 + k];
+            if (r == 0) {
+              acc = v;
+            } else {
+              acc.x += v.x;
+              acc.y += v.y;
+              acc.z += v.z;
+              acc.w += v.w;
+            }
+          }
+        acc.x *= scale;
+        acc.y *= scale;
+        acc.z *= scale;
+        acc.w *= scale;
+        dst[k] = acc;
+      }
+    }
+    fence_proxy_async_smem();  // generic-proxy writes of out[so] -> visible to the bulk-copy engine
+    __syncthreads();           // ... and everybody is done reading ring slot s
+    if (tid == 0) {
+      const long long off4 = base4 + c_begin + (long long)i * kChunk4;
+      for (int q = 0; q < p.world; ++q) {
+        const int r = (p.rank + q) % p.world;  // own copy first, then spread over the links
+        bulk_s2g(reinterpret_cast<float4*>(p.bufs[r] + kArHeaderBytes) + off4, dst, (uint32_t)len4 * 16u);
+      }
+      bulk_commit();
+    }
+  }
+  if (tid == 0) {
+    bulk_wait_all<0>();  // every push has been performed
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  cta_barrier_all_ranks(p, 2, epoch);
+
+  __shared__ int s_ticket;
+  if (tid == 0) s_ticket = atomicAdd(finished, 1);
+  __syncthreads();
+  if (s_ticket == (int)gridDim.x - 1 && tid == 0) {
+    *finished = 0;
+    *epoch_word = epoch;
+  }
+}
+
+template <int W>
+int launch_tma(const ArParams& p, int num_ctas, cudaStream_t stream) {
+  const size_t smem = TmaCfg<W>::kSmem;
+  auto kern = allreduce_tma_kernel<W>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("allreduce: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    return -(int)e;
+  }
+  kern<<<num_ctas, kTmaThreads, smem, stream>>>(p);
+  return launch_status("allreduce_tma_kernel");
+}
+
 }  // namespace
 }  // namespace nafae
 
 using namespace nafae;
+
+NAFAE_CTA_TRACE_READER(nafae_debug_cta_trace_allreduce)
 
 NAFAE_API size_t nafae_ar_buffer_bytes(size_t count_floats, int world) {
   if (world < 1) world = 1;
@@ -238,7 +404,9 @@ NAFAE_API int nafae_ar_close(void* peer_ptr) {
 NAFAE_API int nafae_ar_free(void* dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? 1 : 0; }
 
 NAFAE_API int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t count_floats,
-                                  int num_ctas, cudaStream_t stream) {
+                                  int num_ctas, int cta_threads, cudaStream_t stream) {
+  NAFAE_REQUIRE(cta_threads == 0 || cta_threads == 128 || cta_threads == 256,
+                "allreduce: cta_threads must be 0 (bulk-copy kernel), 128 or 256");
   NAFAE_REQUIRE(bufs && world >= 1 && world <= kArMaxWorld && rank >= 0 && rank < world,
                 "allreduce: bad rank/world (world <= %d)", kArMaxWorld);
   NAFAE_REQUIRE(num_ctas >= 1 && num_ctas <= kArMaxCtas, "allreduce: num_ctas must be in [1, %d]",
@@ -252,6 +420,15 @@ NAFAE_API int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t
   p.rank = rank;
   p.world = world;
   p.count = (long long)count_floats;
-  allreduce_avg_kernel<<<num_ctas, kArThreads, 0, stream>>>(p);
+  static_assert(kArThreadsMax == 256, "flag layout");
+  if (cta_threads == 0) {
+    if (world == 2) return launch_tma<2>(p, num_ctas, stream);
+    if (world <= 4) return launch_tma<4>(p, num_ctas, stream);
+    return launch_tma<8>(p, num_ctas, stream);
+  }
+  if (cta_threads == 128)
+    allreduce_avg_kernel<128><<<num_ctas, 128, 0, stream>>>(p);
+  else
+    allreduce_avg_kernel<256><<<num_ctas, 256, 0, stream>>>(p);
   return launch_status("allreduce_avg_kernel");
 }

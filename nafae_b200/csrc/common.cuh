@@ -28,6 +28,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 int sm_count();  // cached multiprocessor count of the current device
 int persistent_grid();  // sm_count() minus the SMs reserved for concurrent collectives
+void gate_open(void* gate, cudaStream_t stream);  // bump a residency gate's epoch (see header)
 
 // ---------------------------------------------------------------- device side helpers ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -94,6 +95,75 @@ __device__ __forceinline__ int ticket_acq_rel(int* counter) {
   asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
   return old;
 }
+
+// ---------------------------------------------------------------- CTA timeline (debug) ----
+// -DNAFAE_TRACE builds (libnafae_b200_trace.so, tools/timeline.py) record every CTA's start / end
+// (%globaltimer, ns), SM id and two kernel-defined counters; one buffer per translation unit.
+#ifdef NAFAE_TRACE
+struct CtaRec {
+  unsigned long long t0, t1;
+  int kernel, cta, smid, a, b, pad;
+};
+constexpr int kCtaRecMax = 1 << 15;
+static __device__ CtaRec g_cta_rec[kCtaRecMax];
+static __device__ int g_cta_rec_n;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+struct CtaTrace {
+  int idx;
+  __device__ __forceinline__ explicit CtaTrace(int kernel) : idx(-1) {
+    if (threadIdx.x == 0) {
+      idx = atomicAdd(&g_cta_rec_n, 1);
+      if (idx < kCtaRecMax) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        g_cta_rec[idx].t0 = global_ns();
+        g_cta_rec[idx].kernel = kernel;
+        g_cta_rec[idx].cta = blockIdx.x + gridDim.x * blockIdx.y;
+        g_cta_rec[idx].smid = (int)smid;
+        g_cta_rec[idx].a = g_cta_rec[idx].b = 0;
+      }
+    }
+  }
+  // any ONE thread of the CTA may count (thread 0 publishes the slot through shared memory)
+  __device__ __forceinline__ void publish(int* smem_slot) {
+    if (threadIdx.x == 0) *smem_slot = idx;
+  }
+  static __device__ __forceinline__ void count(int slot, int a, int b) {
+    if (slot >= 0 && slot < kCtaRecMax) {
+      g_cta_rec[slot].a += a;
+      g_cta_rec[slot].b += b;
+    }
+  }
+  __device__ __forceinline__ ~CtaTrace() {
+    if (idx >= 0 && idx < kCtaRecMax) g_cta_rec[idx].t1 = global_ns();
+  }
+};
+#define NAFAE_CTA_TRACE(name, kernel) ::nafae::CtaTrace name(kernel)
+#define NAFAE_CTA_TRACE_READER(fn)                                                          \
+  NAFAE_API int fn(void* host_out, int max_recs, int reset) {                                \
+    int n = 0;                                                                               \
+    cudaMemcpyFromSymbol(&n, ::nafae::g_cta_rec_n, sizeof(int));                             \
+    if (n > ::nafae::kCtaRecMax) n = ::nafae::kCtaRecMax;                                    \
+    if (n > max_recs) n = max_recs;                                                          \
+    if (n > 0) cudaMemcpyFromSymbol(host_out, ::nafae::g_cta_rec, sizeof(::nafae::CtaRec) * n); \
+    if (reset) {                                                                             \
+      const int z = 0;                                                                       \
+      cudaMemcpyToSymbol(::nafae::g_cta_rec_n, &z, sizeof(int));                             \
+    }                                                                                        \
+    return n;                                                                                \
+  }
+#else
+struct CtaTrace {
+  __device__ __forceinline__ void publish(int*) {}
+  static __device__ __forceinline__ void count(int, int, int) {}
+};
+#define NAFAE_CTA_TRACE(name, kernel) [[maybe_unused]] ::nafae::CtaTrace name
+#define NAFAE_CTA_TRACE_READER(fn)
+#endif
 
 template <int N>
 __device__ __forceinline__ void bulk_wait_all() {

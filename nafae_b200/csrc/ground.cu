@@ -168,6 +168,7 @@ __device__ void phase2_segment(const FwdParams& p, const Ws& w, int a);
 __device__ void phase3_final(const FwdParams& p, const Ws& w);
 
 __global__ void __launch_bounds__(kFwdThreads, 1) ground_fwd_kernel(const FwdParams p) {
+  NAFAE_CTA_TRACE(cta_trace, 3);
   extern __shared__ __align__(16) float sm[];  // kRowTile * D floats (vis rows of the frame)
   __shared__ int s_ticket;
   __shared__ int s_live[kLiveMax];       // compacted list of live (unmasked) columns
@@ -766,6 +767,7 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 // gather-scale-accumulate over <= F*NQ pairs, not a GEMM.  All cross-CTA inputs are staged into
 // shared memory with one round of independent loads; gather loops issue loads in batches.
 __global__ void __launch_bounds__(kBwdThreads, 1) ground_bwd_kernel(const BwdParams p) {
+  NAFAE_CTA_TRACE(cta_trace, 4);
   extern __shared__ __align__(16) float sm[];
   __shared__ int s_nlive;
   __shared__ int s_ticket;
@@ -1010,6 +1012,7 @@ bool make_dims(int Na, int Ns, int Nb, int Ne, int D, Dims* d) {
 
 using namespace nafae;
 
+NAFAE_CTA_TRACE_READER(nafae_debug_cta_trace_ground)
 #ifdef NAFAE_TRACE
 NAFAE_API int nafae_debug_read_trace(unsigned long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_trace, sizeof(unsigned long long) * 256);

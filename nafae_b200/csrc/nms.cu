@@ -227,6 +227,7 @@ proposal_tail_kernel(const float* __restrict__ proposals, const float* __restric
   __shared__ unsigned long long s_new;
   __shared__ int s_count;
 
+  NAFAE_CTA_TRACE(cta_trace, 2);
   const int f = blockIdx.x, tid = threadIdx.x;
   const int t = tid >> 2, q = tid & 3;  // candidate slot, quarter
   const float* fp = proposals + (size_t)f * n * 4;
@@ -327,6 +328,8 @@ ScratchCache g_nms_scratch;
 }  // namespace nafae
 
 using namespace nafae;
+
+NAFAE_CTA_TRACE_READER(nafae_debug_cta_trace_nms)
 
 NAFAE_API size_t nafae_nms_workspace_bytes(int num_frames, int boxes_num) {
   if (num_frames <= 0 || boxes_num <= 0) return 0;

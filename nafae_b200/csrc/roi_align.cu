@@ -238,13 +238,24 @@ align_bwd_generic(const float* __restrict__ top_diff, const float* __restrict__ 
 // weights are warp-uniform table reads, the taps are LDS with compile-time offsets (W and the
 // padded channel stride are template constants for the two production map sizes), the 2x2 pool is
 // one shuffle per sample row.  For POOL_AVG the 1/4 is folded into the column weights.
+// The kernel is bound by the shared-memory / L1 data stage, not by arithmetic, so two things keep
+// the number of wavefronts down: (a) a sample row whose cell rows equal (or follow by one) the
+// previous sample row's reuses the horizontally interpolated rows it already holds (RoIs shorter
+// than 7 cells -- half of them -- need ~6 row loads instead of 16); (b) the pooled 7x7 blocks of a
+// pass (4*CPL consecutive channels of one RoI = 784*CPL contiguous bytes of the output) are staged
+// in a per-warp shared buffer and leave with ONE bulk store (cp.async.bulk shared -> global)
+// instead of 7*CPL scattered 28-byte-per-channel stores.
 constexpr int kOut = 7;
 constexpr int kS = 8;               // sample grid side
-constexpr int kConsWarps = 16;
+#ifndef NAFAE_CONS_WARPS
+#define NAFAE_CONS_WARPS 16
+#endif
+constexpr int kConsWarps = NAFAE_CONS_WARPS;
 constexpr int kConsThreads = kConsWarps * 32;
 constexpr int kSlabThreads = kConsThreads + 32;  // + producer warp
-constexpr int kMaxRoiTable = 128;   // RoIs of one frame resident in the table at a time
+constexpr int kMaxRoiTable = 104;   // RoIs of one frame resident in the table at a time
 constexpr int kStagesMax = 4;
+constexpr int kPreFrames = 4;      // frames whose RoI tables a CTA may hold at once (prebuilt)
 
 struct __align__(16) RoiEntry {  // 192 B: everything a pass needs about one RoI
   int hoff_b[kS];   // byte offset of row hstart (hstart*W*4); 0 if the sample row is outside
@@ -267,6 +278,7 @@ struct SlabParams {
   int hwp;         // padded per-channel stride in shared memory (floats), hwp % 32 == 8
   int stages;
   int units;       // B * groups
+  int* gate;       // optional residency gate (nafae_gate_wait): [0] arrivals, [1] epoch
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -279,7 +291,8 @@ __device__ __forceinline__ void cons_barrier() {  // the 16 consumer warps only
 template <int POOL, int W_CT, int HWP_CT, int CPL>
 __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const SlabParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [stages][cg][hwp] floats | RoiEntry[kMaxRoiTable] | int roi_id[kMaxRoiTable] | bars
+  // layout: [stages][cg][hwp] floats | RoiEntry[kMaxRoiTable] | int roi_id[kMaxRoiTable] | bars |
+  //         per-warp output staging
   float* slabs = reinterpret_cast<float*>(smem_raw);
   const int W = W_CT ? W_CT : p.W;
   const int hwp = HWP_CT ? HWP_CT : p.hwp;
@@ -288,10 +301,12 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
   int* roi_id = reinterpret_cast<int*>(table + kMaxRoiTable);
   uint64_t* full = reinterpret_cast<uint64_t*>(roi_id + kMaxRoiTable);
   uint64_t* empty = full + kStagesMax;
-  __shared__ int s_nroi, s_next, s_warp_cnt[kConsWarps];
+  float* out_stage = reinterpret_cast<float*>(empty + kStagesMax);  // [kConsWarps][4*CPL][7][7]
+  __shared__ int s_nroi, s_next, s_warp_cnt[kConsWarps], s_fbeg[kPreFrames + 1];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // contiguous unit range per CTA so that the RoI table is rebuilt at most ~twice
+  NAFAE_CTA_TRACE(cta_trace, 1);  // debug builds only
+  // contiguous unit range per CTA: it touches 1-2 frames, whose RoI tables are built once
   const int u_begin = (int)((long long)p.units * blockIdx.x / gridDim.x);
   const int u_end = (int)((long long)p.units * (blockIdx.x + 1) / gridDim.x);
 
@@ -301,6 +316,12 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
       mbar_init(&empty[s], kConsWarps);
     }
     fence_mbar_init();
+    // residency gate: the last CTA to become resident opens it for the concurrent branches
+    if (p.gate != nullptr && atomicAdd(p.gate, 1) == (int)gridDim.x - 1) {
+      p.gate[0] = 0;
+      __threadfence();
+      atomicAdd(p.gate + 1, 1);
+    }
   }
   __syncthreads();
 
@@ -323,62 +344,99 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
   }
 
   // -------------------------------------------------------------- consumer warps ----
+  // Frame ids of RoIs tid, tid + 512, ... stay in registers for the whole kernel: ONE L2 round
+  // trip (in flight while the first slab streams in); every later table scan is register /
+  // shared-memory work only.  (R > kFrCache * 512: scans fall back to global loads.)
+  constexpr int kFrCache = 4;
+  constexpr int kNoFrame = -2147483647 - 1;
+  const bool fr_cached = p.R <= kFrCache * kConsThreads;
+  int fr[kFrCache];
+#pragma unroll
+  for (int i = 0; i < kFrCache; ++i) {
+    const int r = tid + i * kConsThreads;
+    fr[i] = (fr_cached && r < p.R) ? (int)__ldg(p.rois + (size_t)r * 5) : kNoFrame;
+  }
+
   // RoIs whose batch index is outside [0, B): defined as all-zero rows (CTA 0 writes them)
   if (blockIdx.x == 0) {
-    for (int r0 = warp * 32; r0 < p.R; r0 += kConsThreads) {  // one RoI per lane, loads in flight
-      const int r = r0 + lane;
-      const int b = r < p.R ? (int)__ldg(p.rois + (size_t)r * 5) : 0;
-      unsigned bad = __ballot_sync(0xffffffffu, r < p.R && (b < 0 || b >= p.B));
+    auto zero_bad = [&](int base, int b) {  // b = batch index of RoI base + tid
+      unsigned bad = __ballot_sync(0xffffffffu, base + tid < p.R && (b < 0 || b >= p.B));
       while (bad) {
-        const int rr = r0 + __ffs(bad) - 1;
+        const int rr = base + warp * 32 + __ffs(bad) - 1;
         bad &= bad - 1;
         float* o = p.top + (size_t)rr * p.C * (kOut * kOut);
         for (int i = lane; i < p.C * kOut * kOut; i += 32) o[i] = 0.f;
       }
+    };
+    if (fr_cached) {
+#pragma unroll
+      for (int i = 0; i < kFrCache; ++i)
+        if (i * kConsThreads < p.R) zero_bad(i * kConsThreads, fr[i]);
+    } else {
+      for (int base = 0; base < p.R; base += kConsThreads)
+        zero_bad(base, base + tid < p.R ? (int)__ldg(p.rois + (size_t)(base + tid) * 5) : 0);
     }
   }
 
-  // Fill the RoI table with the next (at most kMaxRoiTable) RoIs of frame f whose index is
-  // >= r_start, in ascending index order; s_next = index where the following chunk starts
-  // (>= R when the frame is exhausted).  Called by all consumer warps together.
-  auto build_table = [&](int f, int r_start) {
-    cons_barrier();  // every warp is done with the previous table contents
+  // One 512-RoI step of a table scan: appends the RoIs base + tid (index >= r_start) of frame f
+  // in ascending index order; true when the table is full.  All consumer warps together.
+  auto scan_step = [&](int f, int r_start, int base, int frv) -> bool {
+    const int r = base + tid;
+    const bool hit = r < p.R && r >= r_start && frv == f;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+    cons_barrier();
+    const int have = s_nroi;
+    int before = have, tot = 0;
+    for (int w = 0; w < kConsWarps; ++w) {
+      const int cw = s_warp_cnt[w];
+      if (w < warp) before += cw;
+      tot += cw;
+    }
+    const int pos = before + __popc(bal & ((1u << lane) - 1u));
+    if (hit && pos < kMaxRoiTable) roi_id[pos] = r;
+    if (hit && pos == kMaxRoiTable) s_next = r;  // first RoI that did not fit (unique thread)
+    cons_barrier();
+    if (have + tot >= kMaxRoiTable) {  // uniform
+      if (tid == 0) {
+        s_nroi = kMaxRoiTable;
+        if (have + tot == kMaxRoiTable) s_next = min(base + kConsThreads, p.R);
+      }
+      return true;
+    }
+    if (tid == 0) s_nroi = have + tot;
+    return false;
+  };
+  // Appends (from table position pos0) the RoIs of frame f whose index is >= r_start, at most up
+  // to kMaxRoiTable entries; afterwards s_nroi = entries in the table, s_next = index where the
+  // following chunk starts (>= R when the frame is exhausted).
+  auto scan_frame = [&](int f, int r_start, int pos0) {
+    cons_barrier();  // every warp is done with the previous table contents / counters
     if (tid == 0) {
-      s_nroi = 0;
+      s_nroi = pos0;
       s_next = p.R;
     }
     cons_barrier();
-    for (int base = r_start; base < p.R; base += kConsThreads) {
-      const int r = base + tid;
-      const bool hit = r < p.R && (int)p.rois[(size_t)r * 5] == f;
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-      cons_barrier();
-      const int have = s_nroi;
-      int before = have, tot = 0;
-      for (int w = 0; w < kConsWarps; ++w) {
-        const int cw = s_warp_cnt[w];
-        if (w < warp) before += cw;
-        tot += cw;
+    if (fr_cached) {
+#pragma unroll
+      for (int i = 0; i < kFrCache; ++i) {
+        const int base = i * kConsThreads;
+        if (base >= p.R) break;
+        if (base + kConsThreads <= r_start) continue;
+        if (scan_step(f, r_start, base, fr[i])) break;
       }
-      const int pos = before + __popc(bal & ((1u << lane) - 1u));
-      if (hit && pos < kMaxRoiTable) roi_id[pos] = r;
-      if (hit && pos == kMaxRoiTable) s_next = r;  // first RoI that did not fit (unique thread)
-      cons_barrier();
-      if (have + tot >= kMaxRoiTable) {  // uniform
-        if (tid == 0) {
-          s_nroi = kMaxRoiTable;
-          if (have + tot == kMaxRoiTable) s_next = min(base + kConsThreads, p.R);
-        }
-        break;
+    } else {
+      for (int base = r_start / kConsThreads * kConsThreads; base < p.R; base += kConsThreads) {
+        const int r = base + tid;
+        if (scan_step(f, r_start, base, r < p.R ? (int)p.rois[(size_t)r * 5] : kNoFrame)) break;
       }
-      if (tid == 0) s_nroi = have + tot;
     }
     cons_barrier();
-    const int nroi = s_nroi;
+  };
+  // geometry of table entries [j_lo, j_hi): one thread per (RoI, axis, sample index)
+  auto geometry = [&](int j_lo, int j_hi) {
     const float wscale = POOL == NAFAE_POOL_AVG ? 0.25f : 1.f;
-    // geometry: one thread per (RoI, axis, sample index)
-    for (int e = tid; e < nroi * 2 * kS; e += kConsThreads) {
+    for (int e = j_lo * 2 * kS + tid; e < j_hi * 2 * kS; e += kConsThreads) {
       const int j = e / (2 * kS), k = e % (2 * kS);
       const RoiGeom g = roi_geom(p.rois + (size_t)roi_id[j] * 5, p.scale, kS, kS);
       int cell;
@@ -397,11 +455,38 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
     }
     cons_barrier();
   };
+  auto build_table = [&](int f, int r_start) {  // one (frame, chunk) at a time
+    scan_frame(f, r_start, 0);
+    geometry(0, s_nroi);
+  };
+
+  // Normal case: the RoIs of ALL frames this CTA touches (contiguous unit range: 1-2 frames) fit in
+  // the table together -> built once, here, while the first slab is still in flight; no table work
+  // and no CTA-wide barrier inside the unit loop.  Otherwise: per-(frame, chunk) tables as needed.
+  const int f_first = u_begin / p.groups, f_last = (u_end - 1) / p.groups;
+  bool pre = fr_cached && f_last - f_first < kPreFrames;
+  if (pre) {
+    int pos = 0;
+    for (int f = f_first; f <= f_last; ++f) {
+      if (tid == 0) s_fbeg[f - f_first] = pos;
+      scan_frame(f, 0, pos);
+      if (s_next < p.R) {  // uniform: does not fit
+        pre = false;
+        break;
+      }
+      pos = s_nroi;
+    }
+    if (pre) {
+      if (tid == 0) s_fbeg[f_last - f_first + 1] = pos;
+      geometry(0, pos);
+    }
+  }
 
   int cur_f = -1, cur_start = -1;  // which (frame, chunk start) the table holds
   const int nblk = p.cg / (4 * CPL);  // channel blocks per RoI inside a unit
   const int cq = lane >> 3, pw = lane & 7;
   int g_base = 0;  // running pass-group counter (uniform): deals groups round-robin to warps
+  float* my_stage = out_stage + warp * (4 * CPL * kOut * kOut);
   for (int u = u_begin; u < u_end; ++u) {
     const int it = u - u_begin;
     const int stage = it % p.stages;
@@ -411,20 +496,27 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
     bool waited = false;
     int r_next = 0;
     do {
-      if (!(cur_f == f && cur_start == r_next)) {
-        build_table(f, r_next);
-        cur_f = f;
-        cur_start = r_next;
+      int j0 = 0, nroi, next_after;
+      if (pre) {
+        j0 = s_fbeg[f - f_first];
+        nroi = s_fbeg[f - f_first + 1] - j0;
+        next_after = p.R;
+      } else {
+        if (!(cur_f == f && cur_start == r_next)) {
+          build_table(f, r_next);
+          cur_f = f;
+          cur_start = r_next;
+        }
+        nroi = s_nroi;
+        next_after = s_next;
       }
-      const int nroi = s_nroi;
-      const int next_after = s_next;
       if (!waited) {
         mbar_wait(&full[stage], parity);
         waited = true;
       }
       const int ng = nroi * nblk;
-      for (int idx = (warp - g_base) & (kConsWarps - 1); idx < ng; idx += kConsWarps) {
-        const int j = idx / nblk, blk = idx - j * nblk;
+      for (int idx = warp >= g_base ? warp - g_base : warp - g_base + kConsWarps; idx < ng; idx += kConsWarps) {
+        const int jr = idx / nblk, blk = idx - jr * nblk, j = j0 + jr;
         const RoiEntry& e = table[j];
         const float w0 = e.w0[pw], w1 = e.w1[pw];
         const int ch0 = blk * (4 * CPL) + cq;  // first channel of this lane inside the slab
@@ -440,23 +532,40 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
           h0[v] = a4.x; h0[v + 1] = a4.y; h0[v + 2] = a4.z; h0[v + 3] = a4.w;
           h1[v] = b4.x; h1[v + 1] = b4.y; h1[v + 2] = b4.z; h1[v + 3] = b4.w;
         }
-        float s[CPL][kS];
+        // T0/T1: horizontally interpolated cell rows (hstart, hstart+1) of the current sample row;
+        // kept across sample rows while the cell rows repeat or advance by one (warp-uniform tests)
+        float s[CPL][kS], T0[CPL], T1[CPL];
 #pragma unroll
         for (int ph = 0; ph < kS; ++ph) {
-          const unsigned char* t = lane_base + hoff[ph];
+          const int d = ph ? hoff[ph] - hoff[ph - 1] : -1;
+          if (d != 0) {
+            const unsigned char* t = lane_base + hoff[ph];
+            if (d == W * 4) {
 #pragma unroll
-          for (int k = 0; k < CPL; ++k) {
-            const float* q = reinterpret_cast<const float*>(t + (size_t)k * 4 * hwp * 4);
-            const float top = fmaf(q[1], w1, q[0] * w0);
-            const float bot = fmaf(q[W + 1], w1, q[W] * w0);
-            s[k][ph] = fmaf(bot, h1[ph], top * h0[ph]);
+              for (int k = 0; k < CPL; ++k) T0[k] = T1[k];
+            } else {
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) {
+                const float* q = reinterpret_cast<const float*>(t + (size_t)k * 4 * hwp * 4);
+                T0[k] = fmaf(q[1], w1, q[0] * w0);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+              const float* q = reinterpret_cast<const float*>(t + (size_t)k * 4 * hwp * 4);
+              T1[k] = fmaf(q[W + 1], w1, q[W] * w0);
+            }
           }
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) s[k][ph] = fmaf(T1[k], h1[ph], T0[k] * h0[ph]);
         }
-        const int c_first = gidx * p.cg + ch0;
-        float* o = p.top + ((size_t)roi_id[j] * p.C + c_first) * (kOut * kOut) + pw;
+        // pooled block -> per-warp staging (channel-major like the output) -> one bulk store
+        if (lane == 0) bulk_wait_read<0>();  // the previous pass's store has drained the buffer
+        __syncwarp();
+        float* o = my_stage + cq * (kOut * kOut) + pw;
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
-          float* ok = o + (size_t)k * 4 * (kOut * kOut);
+          float* ok = o + k * 4 * (kOut * kOut);
           if (POOL == NAFAE_POOL_AVG) {
             float hs_prev = s[k][0] + __shfl_down_sync(0xffffffffu, s[k][0], 1);
 #pragma unroll
@@ -476,14 +585,23 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
             }
           }
         }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
+        __syncwarp();
+        if (lane == 0) {
+          const int c_first = gidx * p.cg + blk * (4 * CPL);
+          bulk_s2g(p.top + ((size_t)roi_id[j] * p.C + c_first) * (kOut * kOut), my_stage,
+                   (uint32_t)(4 * CPL * kOut * kOut * sizeof(float)));
+          bulk_commit();
+        }
       }
-      g_base += ng;
+      g_base = (g_base + ng) % kConsWarps;  // warp that takes the next pass-group
       r_next = next_after;
     } while (r_next < p.R);
 
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);  // this warp is done with the stage
   }
+  if (lane == 0) bulk_wait_all<0>();  // staging buffer must outlive the last bulk store
 }
 
 int smem_optin_limit() {
@@ -516,15 +634,18 @@ int launch_slab(const SlabParams& p, int pool, size_t smem, cudaStream_t stream)
 // Returns 1 if the slab kernel was launched, 0 if the shape is not eligible (caller falls back),
 // <0 on a launch error.
 int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W, int C, int pool,
-                    const float* rois, float* top, cudaStream_t stream) {
+                    const float* rois, float* top, int* gate, cudaStream_t stream) {
   const int hw = H * W;
   if (hw % 4 != 0 || C % 8 != 0 || H < 2 || W < 2) return 0;
   if ((reinterpret_cast<uintptr_t>(bottom) & 15) != 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(top) & 15) != 0) return 0;  // bulk stores of the pooled blocks
   if ((long long)R * 5 >= (1ll << 31)) return 0;
   int hwp = hw;
   while (hwp % 32 != 8) hwp += 4;
+  const bool small_map = W == 14 && hwp == 200 && C % 32 == 0;  // 14x14: 16-channel passes (CPL 4)
+  const size_t staging = (size_t)kConsWarps * 4 * (small_map ? 4 : 2) * kOut * kOut * sizeof(float);
   const size_t fixed = sizeof(RoiEntry) * kMaxRoiTable + sizeof(int) * kMaxRoiTable +
-                       sizeof(uint64_t) * 2 * kStagesMax + 128;
+                       sizeof(uint64_t) * 2 * kStagesMax + staging + 128;
   const size_t budget = (size_t)smem_optin_limit() - 1024;  // static smem + slack
   int cg = 0, stages = 0;
   // prefer >= 3 stages with a slab of <= 64 KB
@@ -558,9 +679,10 @@ int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W
   p.hwp = hwp;
   p.stages = stages;
   p.units = B * p.groups;
+  p.gate = gate;
   const size_t smem = (size_t)cg * hwp * 4 * stages + fixed;
   if (W == 50 && hwp == 1928) return launch_slab<50, 1928, 2>(p, pool, smem, stream);  // 38x50 maps
-  if (W == 14 && hwp == 200 && cg == 32) return launch_slab<14, 200, 4>(p, pool, smem, stream);  // 14x14
+  if (small_map && cg == 32) return launch_slab<14, 200, 4>(p, pool, smem, stream);  // 14x14
   return launch_slab<0, 0, 2>(p, pool, smem, stream);
 }
 
@@ -577,10 +699,13 @@ int grid_for(long long total) {
 
 using namespace nafae;
 
+NAFAE_CTA_TRACE_READER(nafae_debug_cta_trace_roi_align)
+
 NAFAE_API size_t nafae_roi_align_workspace_bytes(int batch_size, int num_rois) {
   (void)batch_size;
   (void)num_rois;
-  return 0;  // the RoI-per-frame lists live in shared memory; no device scratch needed
+  // optional: the residency gate (the RoI tables live in shared memory)
+  return NAFAE_ROI_ALIGN_WS_BYTES;
 }
 
 NAFAE_API int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size,
@@ -589,24 +714,30 @@ NAFAE_API int nafae_roi_align_forward(const float* bottom_data, float spatial_sc
                                       const float* bottom_rois, float* top_data, unsigned flags,
                                       void* workspace, size_t workspace_bytes,
                                       cudaStream_t stream) {
-  (void)workspace;
-  (void)workspace_bytes;
+  NAFAE_REQUIRE(workspace == nullptr || workspace_bytes == 0 ||
+                    workspace_bytes >= NAFAE_ROI_ALIGN_WS_BYTES,
+                "roi_align: workspace must be NULL or >= %d bytes", NAFAE_ROI_ALIGN_WS_BYTES);
+  int* gate = workspace != nullptr && workspace_bytes > 0 ? static_cast<int*>(workspace) : nullptr;
   NAFAE_REQUIRE(batch_size >= 0 && num_rois >= 0 && channels >= 0, "roi_align: negative sizes");
   NAFAE_REQUIRE(pool_mode >= NAFAE_POOL_NONE && pool_mode <= NAFAE_POOL_MAX,
                 "roi_align: bad pool_mode %d", pool_mode);
   NAFAE_REQUIRE(out_height >= 1 && out_width >= 1, "roi_align: bad output size %dx%d", out_height,
                 out_width);
   const long long total = (long long)num_rois * channels * out_height * out_width;
-  if (total == 0) return 1;
+  if (total == 0) {
+    if (gate) gate_open(gate, stream);
+    return 1;
+  }
   NAFAE_REQUIRE(height >= 2 && width >= 2, "roi_align: feature map must be at least 2x2");
   NAFAE_REQUIRE(bottom_data && bottom_rois && top_data, "roi_align: NULL buffer");
   const bool exact = (flags & NAFAE_FLAG_EXACT) != 0;
   if (!exact && pool_mode != NAFAE_POOL_NONE && out_height == kOut && out_width == kOut &&
       batch_size > 0) {
     const int st = try_launch_slab(bottom_data, spatial_scale, batch_size, num_rois, height, width,
-                                   channels, pool_mode, bottom_rois, top_data, stream);
+                                   channels, pool_mode, bottom_rois, top_data, gate, stream);
     if (st != 0) return st;
   }
+  if (gate) gate_open(gate, stream);  // no persistent kernel on this path: nothing to wait for
   const int grid = grid_for(total);
   if (exact)
     align_fwd_generic<true><<<grid, 256, 0, stream>>>(bottom_data, spatial_scale, batch_size, total,

@@ -41,7 +41,37 @@ int persistent_grid() {
   return n < 1 ? 1 : n;
 }
 
+// gate layout (ints): [0] arrivals of the current launch, [1] epoch, [2 + slot] epochs seen by slot
+__global__ void gate_wait_kernel(int* gate, int slot) {
+  NAFAE_CTA_TRACE(cta_trace, 6);
+  if (threadIdx.x == 0) {
+    const int seen = gate[2 + slot];
+    int epoch;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(epoch) : "l"(gate + 1) : "memory");
+      if (epoch == seen) __nanosleep(200);
+    } while (epoch == seen);
+    gate[2 + slot] = epoch;
+  }
+}
+
+__global__ void gate_open_kernel(int* gate) {  // paths that do not run the persistent kernel
+  if (threadIdx.x == 0) atomicAdd(gate + 1, 1);
+}
+
+void gate_open(void* gate, cudaStream_t stream) {
+  gate_open_kernel<<<1, 32, 0, stream>>>(static_cast<int*>(gate));
+}
+
 }  // namespace nafae
+
+NAFAE_CTA_TRACE_READER(nafae_debug_cta_trace_runtime)
+
+NAFAE_API int nafae_gate_wait(void* gate, int slot, cudaStream_t stream) {
+  NAFAE_REQUIRE(gate != nullptr && slot >= 0 && slot < 6, "gate_wait: bad gate/slot");
+  nafae::gate_wait_kernel<<<1, 32, 0, stream>>>(static_cast<int*>(gate), slot);
+  return nafae::launch_status("gate_wait_kernel");
+}
 
 NAFAE_API int nafae_set_reserved_sms(int n) {
   const int prev = nafae::g_reserved_sms;

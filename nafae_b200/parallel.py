@@ -13,7 +13,9 @@ import torch
 import torch.distributed as dist
 
 
-COMM_SMS = int(os.environ.get("NAFAE_COMM_SMS", "16"))  # SMs left to the collective while the slab kernel runs
+# SMs left to the collective while the slab kernel runs -- NCCL and the 256-thread peer-memory
+# all-reduce only; the default 128-thread variant co-resides with the slab CTAs and needs none
+COMM_SMS = int(os.environ.get("NAFAE_COMM_SMS", "16"))
 
 
 def trainable_grad_elems(vis_fc_dim=4096, glove_dim=200, ebd_dim=512):
@@ -116,7 +118,7 @@ class PeerAllReduce(object):
     every rank must call it the same number of times.  torch.distributed is only used once, to
     exchange the 64-byte IPC handles."""
 
-    def __init__(self, numel, device, rank=None, world=None, num_ctas=None):
+    def __init__(self, numel, device, rank=None, world=None, num_ctas=None, cta_threads=None):
         import ctypes
         from . import _C
         self._C, self._ct = _C, ctypes
@@ -126,7 +128,12 @@ class PeerAllReduce(object):
         pad = 4 * self.world
         self.count = (int(numel) + pad - 1) // pad * pad
         self.numel = int(numel)
-        self.num_ctas = int(num_ctas if num_ctas is not None else os.environ.get("NAFAE_AR_CTAS", "96"))
+        # cta_threads 0 = bulk-copy (TMA) kernel, one CTA per SM left free by nafae_set_reserved_sms;
+        # 256 / 128 = per-thread-load kernels; see csrc/allreduce.cu
+        self.cta_threads = int(cta_threads if cta_threads is not None else
+                               os.environ.get("NAFAE_AR_THREADS", "0"))
+        self.num_ctas = int(num_ctas if num_ctas is not None else
+                            os.environ.get("NAFAE_AR_CTAS", {0: str(COMM_SMS), 128: "128"}.get(self.cta_threads, "96")))
         nbytes = int(_C.lib.nafae_ar_buffer_bytes(self.count, self.world))
         own = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * 64)()
@@ -168,7 +175,8 @@ class PeerAllReduce(object):
             return
         with torch.cuda.device(self.dev):
             st = self._C.lib.nafae_allreduce_avg(self._ptrs, self.rank, self.world, self.count,
-                                                 self.num_ctas, self._C.stream(self.dev))
+                                                 self.num_ctas, self.cta_threads,
+                                                 self._C.stream(self.dev))
         self._C.check(st, "nafae_allreduce_avg")
 
     def close(self):

@@ -10,7 +10,11 @@ and ``nafae_b200.grounding`` are the drop-in, autograd-friendly form of the same
 """
 import torch
 
+import os
+
 from . import _C
+
+_NO_WS = bool(int(os.environ.get("NAFAE_NO_ALIGN_WS", "0")))  # dev switch: no gate signalling
 
 
 class GroundingStep(object):
@@ -46,6 +50,8 @@ class GroundingStep(object):
         self.grad_word = torch.empty((self.NQ, D), **f32)
         nbytes = int(_C.lib.nafae_ground_workspace_bytes(*self.dims))
         self.ws = torch.zeros((nbytes // 4,), dtype=torch.int32, device=self.dev)
+        # RoIAlign workspace: the persistent kernel's residency gate (include/nafae_b200.h)
+        self.gate = torch.zeros((_C.ROI_ALIGN_WS_BYTES // 4,), dtype=torch.int32, device=self.dev)
         self.graph = None
 
     # -- input staging ---------------------------------------------------------------------
@@ -80,14 +86,23 @@ class GroundingStep(object):
                                            P(self.roi_scores), None, _C.stream(self.dev)),
                      "nafae_proposal_tail")
 
-    def run_align(self):
-        """RoIAlignAvg 7x7 of the current rois -> pooled (R, C, 7, 7)."""
+    def run_align(self, gated=True):
+        """RoIAlignAvg 7x7 of the current rois -> pooled (R, C, 7, 7).  gated: `self.gate` opens once
+        all persistent CTAs of the kernel are resident (concurrent branches may `wait_gate` on it)."""
         L, P = _C.lib, _C.ptr
+        gated = gated and not _NO_WS
         with torch.cuda.device(self.dev):
             _C.check(L.nafae_roi_align_forward(P(self.features), self.scale, self.F, self.R, self.H,
                                                self.W, self.C, 7, 7, _C.POOL_AVG, P(self.rois),
-                                               P(self.pooled), 0, None, 0, _C.stream(self.dev)),
+                                               P(self.pooled), 0, P(self.gate) if gated else None,
+                                               _C.ROI_ALIGN_WS_BYTES if gated else 0, _C.stream(self.dev)),
                      "nafae_roi_align_forward")
+
+    def wait_gate(self, slot):
+        """Hold the current stream until this step's gated RoIAlign kernel owns its SMs."""
+        with torch.cuda.device(self.dev):
+            _C.check(_C.lib.nafae_gate_wait(_C.ptr(self.gate), int(slot), _C.stream(self.dev)),
+                     "nafae_gate_wait")
 
     def run_detector(self):
         """Detector-side half: proposal tail -> RoIAlignAvg.  Frozen in NAFAE (model.py:651,673,
@@ -140,7 +155,7 @@ class GroundingStep(object):
         self.graph.replay()
 
 
-def capture_pipelined(align_step, next_step, streams, extra_branch=None):
+def capture_pipelined(align_step, next_step, streams, extra_branch=None, gate_head=False):
     """CUDA graph of one software-pipelined training step (three concurrent branches):
 
         A (capturing stream): RoIAlign of `align_step`        -- batch k+1, rois from the last replay
@@ -153,25 +168,36 @@ def capture_pipelined(align_step, next_step, streams, extra_branch=None):
     Every replay executes exactly one proposal tail, one RoIAlign and one head; dependencies inside
     a batch (tail -> RoIAlign through `rois`, fwd -> bwd) are preserved because graphs serialise
     and the two buffer sets alternate.  The slab kernel is persistent: leave a few SMs to the head
-    kernels with `nafae_set_reserved_sms` (the tail's small CTAs co-reside with it)."""
+    kernels with `nafae_set_reserved_sms` (the tail's small CTAs co-reside with it).
+
+    All branches start at the same instant and the block scheduler places CTAs breadth-first, so
+    the head's first kernel lands on every SM and the 210 KB persistent RoIAlign CTAs start late
+    on the SMs where its long-lived CTAs sit.  A branch that must NOT spread over the GPU (the
+    all-reduce: its CTAs spin on peers) waits behind the kernel's residency gate (`wait_gate`);
+    `gate_head=True` does the same for the head (measured slower: its kernels want the whole GPU)."""
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        capture_pipelined_body(align_step, next_step, streams, extra_branch)
+        capture_pipelined_body(align_step, next_step, streams, extra_branch, gate_head)
     return g
 
 
-def capture_pipelined_body(align_step, next_step, streams, extra_branch=None):
+def capture_pipelined_body(align_step, next_step, streams, extra_branch=None, gate_head=False):
     """The fork / join of one pipelined step on the capturing stream (call inside torch.cuda.graph;
     several bodies in a row make a multi-step graph that amortises the graph-launch latency)."""
     cur = torch.cuda.current_stream()
     joined = []
-    for st, fn in ((streams[0], next_step.run_tail), (streams[1], next_step.run_head)):
+
+    def head():
+        if gate_head:
+            align_step.wait_gate(0)
+        next_step.run_head()
+    for st, fn in ((streams[0], next_step.run_tail), (streams[1], head)):
         st.wait_stream(cur)
         with torch.cuda.stream(st):
             fn()
         joined.append(st)
     if extra_branch is not None:
-        extra_stream = extra_branch(cur)
+        extra_stream = extra_branch(cur)  # a gated extra branch calls align_step.wait_gate(1) itself
         if extra_stream is not None:
             joined.append(extra_stream)
     align_step.run_align()

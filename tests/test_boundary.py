@@ -130,6 +130,6 @@ def test_allreduce_abi_argument_checks_without_a_gpu():
     assert _C.lib.nafae_ar_buffer_bytes(n, 8) >= n * 4 + _C.lib.nafae_ar_data_offset()
     assert _C.lib.nafae_ar_buffer_bytes(5, 8) == _C.lib.nafae_ar_data_offset() + 32 * 4  # padded to 4*world
     ptrs = (ctypes.c_void_p * 2)()
-    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 9, 64, 8, None) == 0        # world > 8
-    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 2, 10, 8, None) == 0        # count not padded
-    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 1, 64, 8, None) == 1        # world 1: nothing to do
+    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 9, 64, 8, 128, None) == 0        # world > 8
+    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 2, 10, 8, 128, None) == 0        # count not padded
+    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 1, 64, 8, 256, None) == 1        # world 1: nothing to do

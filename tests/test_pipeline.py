@@ -166,8 +166,43 @@ def test_symmetric_buffer_alloc_and_world1_allreduce_is_identity():
     assert float(buf.abs().sum()) == 0.0  # zero-filled
     buf.copy_(torch.arange(n, dtype=torch.float32, device="cuda:0"))
     ptrs = (ctypes.c_void_p * 1)(own.value)
-    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 1, n, 8, _C.stream()) == 1
+    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 1, n, 8, 128, _C.stream()) == 1
     torch.cuda.synchronize()
     assert torch.equal(buf.cpu(), torch.arange(n, dtype=torch.float32))
     del buf
     assert _C.lib.nafae_ar_free(own) == 1
+
+
+@gpu
+def test_residency_gate_orders_a_concurrent_branch_behind_the_roi_align_kernel():
+    """nafae_gate_wait: a branch on another stream is released by every gated RoIAlign launch (slab
+    kernel and generic-kernel fallback alike), repeatedly, without changing the pooled features."""
+    from nafae_b200 import _C
+    from nafae_b200.pipeline import GroundingStep
+    dev = torch.device("cuda:0")
+    for cfg_name, shape in (("slab", (4, 64, 38, 50)), ("generic_fallback", (2, 6, 37, 50))):
+        F, C, H, W = shape
+        c = dict(synth.CONFIGS["cfg2"], Na=1, Ns=F, C=C, H=H, W=W, n=300, img_h=H * 16, img_w=W * 16)
+        st = GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], C, H, W, c["n"], device=dev)
+        st.load(synth.make_batch(c, 11))
+        st.run_tail()
+        st.run_align(gated=False)
+        torch.cuda.synchronize()
+        want = st.pooled.clone()
+        st.pooled.zero_()
+        side = torch.cuda.Stream(dev)
+        marks = torch.zeros(3, device=dev)
+        for it in range(3):  # several rounds: the gate re-arms itself
+            with torch.cuda.stream(side):
+                st.wait_gate(0)          # enqueued BEFORE the kernel that opens the gate
+                marks[it] = 1.0
+            st.run_align(gated=True)
+            torch.cuda.synchronize()
+            assert float(marks[it]) == 1.0, cfg_name
+        assert torch.equal(st.pooled, want), cfg_name
+    # argument checks: slot range, NULL gate, undersized workspace
+    assert _C.lib.nafae_gate_wait(None, 0, _C.stream()) == 0
+    assert _C.lib.nafae_gate_wait(_C.ptr(st.gate), 9, _C.stream()) == 0
+    assert _C.lib.nafae_roi_align_forward(_C.ptr(st.features), st.scale, st.F, st.R, st.H, st.W, st.C, 7, 7,
+                                          _C.POOL_AVG, _C.ptr(st.rois), _C.ptr(st.pooled), 0,
+                                          _C.ptr(st.gate), 8, _C.stream()) == 0

@@ -5,7 +5,8 @@ from nafae_b200 import parallel
 rank, world, local = parallel.init_from_env()
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-n = parallel.trainable_grad_elems()
+n = int(os.environ.get("N_FLOATS", parallel.trainable_grad_elems()))
+n = (n + 4 * world - 1) // (4 * world) * (4 * world)
 ar = parallel.PeerAllReduce(n, dev)
 torch.manual_seed(100 + rank)
 ok = True
@@ -44,4 +45,16 @@ if rank == 0:
     print("world %d peer all-reduce %.1f MB, %d CTAs: %.1f us (graph replay)  ok=%s" % (
         world, n * 4 / 1e6, ar.num_ctas, e0.elapsed_time(e1) / 200 * 1e3, ok), flush=True)
 ar.close()
+if rank == 0 and os.environ.get("P2P_BW") and torch.cuda.device_count() > 1:
+    a = torch.empty(64 << 20, dtype=torch.uint8, device="cuda:0")
+    b = torch.empty(64 << 20, dtype=torch.uint8, device="cuda:1")
+    for _ in range(3):
+        a.copy_(b)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        a.copy_(b)
+    e1.record()
+    torch.cuda.synchronize()
+    print("p2p copy cuda:1 -> cuda:0, 64 MiB: %.0f GB/s" % (10 * (64 << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9), flush=True)
 dist.destroy_process_group()
