@@ -26,6 +26,7 @@
 // gate (nafae_gate_wait): started at the same instant, its CTAs would land on every SM first and
 // keep the 210 KB persistent CTAs out until the whole all-reduce has finished.
 // The kernel has no host-side state (the epoch lives in the buffer): it is CUDA-graph capturable.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -422,8 +423,10 @@ NAFAE_API int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t
   p.count = (long long)count_floats;
   static_assert(kArThreadsMax == 256, "flag layout");
   if (cta_threads == 0) {
-    if (world == 2) return launch_tma<2>(p, num_ctas, stream);
-    if (world <= 4) return launch_tma<4>(p, num_ctas, stream);
+    int width = world;  // template bound on the world size; NAFAE_AR_FORCE_W widens it (dev/test)
+    if (const char* f = getenv("NAFAE_AR_FORCE_W")) width = atoi(f) > world ? atoi(f) : world;
+    if (width == 2) return launch_tma<2>(p, num_ctas, stream);
+    if (width <= 4) return launch_tma<4>(p, num_ctas, stream);
     return launch_tma<8>(p, num_ctas, stream);
   }
   if (cta_threads == 128)

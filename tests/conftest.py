@@ -19,6 +19,14 @@ def pytest_collection_modifyitems(config, items):
     except Exception:  # pragma: no cover
         has_gpu = False
     if has_gpu:
+        # a kernel that never finishes must not hang the box: bound every GPU test
+        try:
+            import pytest_timeout  # noqa: F401
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(240, method="thread"))
+        except ImportError:  # pragma: no cover
+            pass
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

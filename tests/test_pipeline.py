@@ -174,9 +174,13 @@ def test_symmetric_buffer_alloc_and_world1_allreduce_is_identity():
 
 
 @gpu
-def test_residency_gate_orders_a_concurrent_branch_behind_the_roi_align_kernel():
+@pytest.mark.timeout(100, method="thread")
+def test_residency_gate_releases_a_concurrent_branch():
     """nafae_gate_wait: a branch on another stream is released by every gated RoIAlign launch (slab
-    kernel and generic-kernel fallback alike), repeatedly, without changing the pooled features."""
+    kernel and generic-kernel fallback alike), repeatedly, without changing the pooled features.
+    (The wait-enqueued-before-the-opener order is what the pipelined step graphs of bench.py use;
+    on eager streams a spinning kernel must never precede the FIRST use of another kernel -- lazy
+    module loading may synchronise the device -- so here the opener is always enqueued first.)"""
     from nafae_b200 import _C
     from nafae_b200.pipeline import GroundingStep
     dev = torch.device("cuda:0")
@@ -189,17 +193,18 @@ def test_residency_gate_orders_a_concurrent_branch_behind_the_roi_align_kernel()
         st.run_align(gated=False)
         torch.cuda.synchronize()
         want = st.pooled.clone()
-        st.pooled.zero_()
         side = torch.cuda.Stream(dev)
-        marks = torch.zeros(3, device=dev)
-        for it in range(3):  # several rounds: the gate re-arms itself
-            with torch.cuda.stream(side):
-                st.wait_gate(0)          # enqueued BEFORE the kernel that opens the gate
-                marks[it] = 1.0
+        marks = torch.zeros(4, device=dev)
+        for it in range(4):  # several rounds: the gate re-arms itself
+            st.pooled.zero_()
             st.run_align(gated=True)
+            with torch.cuda.stream(side):
+                st.wait_gate(0)
+                marks[it:it + 1].fill_(1.0)  # device-side fill: nothing here may block the host
             torch.cuda.synchronize()
             assert float(marks[it]) == 1.0, cfg_name
-        assert torch.equal(st.pooled, want), cfg_name
+            assert torch.equal(st.pooled, want), cfg_name
+        assert int(st.gate[1]) == 4 and int(st.gate[2]) == 4 and int(st.gate[0]) == 0, cfg_name
     # argument checks: slot range, NULL gate, undersized workspace
     assert _C.lib.nafae_gate_wait(None, 0, _C.stream()) == 0
     assert _C.lib.nafae_gate_wait(_C.ptr(st.gate), 9, _C.stream()) == 0
