@@ -211,6 +211,10 @@ def run_ours(args):
     from nafae_b200 import synth, parallel
     from nafae_b200.pipeline import GroundingStep
 
+    # NCCL prints its version banner on stdout at communicator creation: keep stdout for the ONE JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = parallel.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -236,6 +240,12 @@ def run_ours(args):
             buckets = [parallel.PeerAllReduce(parallel.trainable_grad_elems(), dev) for _ in range(2)]
         for st, b in zip(steps, buckets):
             st.grad_word = b.views([(st.NQ, c["D"])])[0]
+    if world > 1:
+        dist.barrier()  # communicator fully initialised (banner printed) on every rank
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     from nafae_b200 import _C
     from nafae_b200.pipeline import capture_pipelined, capture_pipelined_body
     pipelined = not args.no_pipeline
@@ -444,6 +454,9 @@ def run_ours(args):
                                        "NMS/RoIAlign, launched behind the RoIAlign kernel's residency gate); "
                                        "%d SMs left free for it"
                                        % ("NCCL" if args.nccl_allreduce else
+                                          ("fused two-shot NVLink peer-memory kernel (allreduce_tma_kernel: bulk-copy pull, "
+                                           "reduce, bulk-copy push; %d CTAs)" % buckets[0].num_ctas)
+                                          if buckets[0].cta_threads == 0 else
                                           "two-shot NVLink peer-memory kernel (allreduce_avg_kernel, %d CTAs x %d threads)"
                                           % (buckets[0].num_ctas, buckets[0].cta_threads),
                                           parallel.trainable_grad_elems(), parallel.trainable_grad_elems() * 4 / 1e6,
