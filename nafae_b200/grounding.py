@@ -176,3 +176,25 @@ def record_det(img_inds, obj_labels, obj_bboxes, obj_confs, Nb, vid_entities, D,
                 obj_labels.append(entity)
                 obj_bboxes.append(infer_boxes[box_id_offset])
                 obj_confs.append(D_sim[act_ind][spl_ind][ent_ind])
+
+
+def record_det_tensors(D, D_sim, entities_length, img_ids, infer_boxes, Nb):
+    """Device-resident, loop-free form of `record_det` (model.py:477-487) for the evaluation sweep:
+    every (segment a, frame s, entity e < entities_length[a]) in the reference's append order
+    (a, then s, then e) as tensors on D's device.
+
+    D, D_sim: (Na, Ns, Ne) from `postprocess` (global box rows / similarities); img_ids: (F,)
+    integer tensor (one id per frame row); infer_boxes: (R, 4).  Returns
+    ``(img_inds, seg_idx, ent_idx, boxes, confs)``: `vid_entities[seg_idx[i]][ent_idx[i]]` is the
+    label the reference appends for row i.  No host synchronisation except the final sizes."""
+    Na, Ns, Ne = D.shape
+    dev = D.device
+    lens = _lens_tensor(entities_length, dev).to(torch.int64)
+    ent = torch.arange(Ne, device=dev)
+    keep = (ent.view(1, 1, Ne) < lens.view(Na, 1, 1)).expand(Na, Ns, Ne)
+    rows = D[keep].to(torch.int64)                      # row-major: a, s, e -- the reference's order
+    seg_idx = torch.arange(Na, device=dev).view(Na, 1, 1).expand(Na, Ns, Ne)[keep]
+    ent_idx = ent.view(1, 1, Ne).expand(Na, Ns, Ne)[keep]
+    img_inds = torch.as_tensor(img_ids, device=dev)[torch.div(rows, int(Nb), rounding_mode="floor")]
+    boxes = torch.as_tensor(infer_boxes, device=dev)[rows]
+    return img_inds, seg_idx, ent_idx, boxes, D_sim[keep]
