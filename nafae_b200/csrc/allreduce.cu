@@ -423,8 +423,11 @@ NAFAE_API int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t
   p.count = (long long)count_floats;
   static_assert(kArThreadsMax == 256, "flag layout");
   if (cta_threads == 0) {
-    int width = world;  // template bound on the world size; NAFAE_AR_FORCE_W widens it (dev/test)
-    if (const char* f = getenv("NAFAE_AR_FORCE_W")) width = atoi(f) > world ? atoi(f) : world;
+    // template bound on the world size.  Measured on B200 boxes: <2> at world 2, <8> at world 8;
+    // worlds 3..7 run the <8> instantiation (same code, smaller chunks) until <4> has been on
+    // hardware -- NAFAE_AR_FORCE_W=4 selects it (dev/test).
+    int width = world == 2 ? 2 : 8;
+    if (const char* f = getenv("NAFAE_AR_FORCE_W")) width = atoi(f) >= world ? atoi(f) : width;
     if (width == 2) return launch_tma<2>(p, num_ctas, stream);
     if (width <= 4) return launch_tma<4>(p, num_ctas, stream);
     return launch_tma<8>(p, num_ctas, stream);
