@@ -31,7 +31,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t; /* same opaque handle as CUDA driver_types.h */
 #endif
 
-#define NAFAE_B200_ABI_VERSION 1
+#define NAFAE_B200_ABI_VERSION 2 /* 2: nafae_gate_wait, nafae_allreduce_avg(cta_threads) */
 
 /* pooling applied on top of the sampled RoIAlign grid (modules/roi_align.py:6-42) */
 #define NAFAE_POOL_NONE 0 /* RoIAlign    : output is the aligned_height x aligned_width grid   */

@@ -76,6 +76,11 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
+ABI_VERSION = 2  # include/nafae_b200.h NAFAE_B200_ABI_VERSION this host code was written against
+if not MISSING and int(lib.nafae_abi_version()) != ABI_VERSION:
+    raise ImportError("%s has ABI version %d, this package needs %d: rebuild it (make -C nafae_b200/csrc)"
+                      % (LIB_PATH, int(lib.nafae_abi_version()), ABI_VERSION))
+
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 FLAG_EXACT = 1
 GATE_BYTES = 32

@@ -10,11 +10,7 @@ and ``nafae_b200.grounding`` are the drop-in, autograd-friendly form of the same
 """
 import torch
 
-import os
-
 from . import _C
-
-_NO_WS = bool(int(os.environ.get("NAFAE_NO_ALIGN_WS", "0")))  # dev switch: no gate signalling
 
 
 class GroundingStep(object):
@@ -90,7 +86,6 @@ class GroundingStep(object):
         """RoIAlignAvg 7x7 of the current rois -> pooled (R, C, 7, 7).  gated: `self.gate` opens once
         all persistent CTAs of the kernel are resident (concurrent branches may `wait_gate` on it)."""
         L, P = _C.lib, _C.ptr
-        gated = gated and not _NO_WS
         with torch.cuda.device(self.dev):
             _C.check(L.nafae_roi_align_forward(P(self.features), self.scale, self.F, self.R, self.H,
                                                self.W, self.C, 7, 7, _C.POOL_AVG, P(self.rois),

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     assert not _C.MISSING
     assert set(_declared_symbols()) == set(_C.SIGNATURES), "ctypes table out of sync with the header"
-    assert lib.nafae_abi_version() == 1
+    assert lib.nafae_abi_version() == 2
 
 
 def test_invalid_arguments_return_zero_without_a_gpu():

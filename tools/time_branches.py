@@ -81,9 +81,7 @@ def capture(sub, j, res):
 
 
 variants = [("A", 0), ("A", reserve), ("AC", reserve), ("ABC", reserve)]
-variants += [("gate0", res) for res in (8, 24)]
-if not os.environ.get("NAFAE_NO_ALIGN_WS"):
-    variants += [("gate1", res) for res in (16, 32)]
+variants += [("gate0", res) for res in (8, 24)] + [("gate1", res) for res in (16, 32)]
 for sub, res in variants:
     if sub.startswith("gate"):
         gs = [capture3(j, res, sub[-1] == "1") for j in range(2)]
