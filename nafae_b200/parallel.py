@@ -53,6 +53,20 @@ def shard_segments(num_segments, rank, world):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def gather_dets(dets):
+    """Inference sweep: every rank grounds its own contiguous shard of the
+    segment list (`shard_segments`) and records detections with GLOBAL image ids; this merges the
+    four parallel lists `[img_ids, labels, boxes, confs]` of all ranks in rank order -- the same lists
+    a single process walking the segments in order would have produced (model.py:972), ready for
+    `evaluate.evaluate_box` / `evaluate.save_dets`.  One `all_gather_object` (any backend); returns the
+    merged lists on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [list(x) for x in dets]
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, [list(x) for x in dets])
+    return [[item for part in parts for item in part[k]] for k in range(4)]
+
+
 class GradBucket(object):
     """Flat fp32 gradient bucket with an overlapped all-reduce.
 

@@ -68,3 +68,37 @@ def test_trainable_grad_bucket_size_matches_reference_parameter_shapes():
     # vis_ebd.fc1 (512x4096 + 512), word_ebd.fc1 (512x200 + 512), word_ebd.bn (2x512): model.py:616-642
     assert parallel.trainable_grad_elems() == 512 * 4096 + 512 + 512 * 200 + 512 + 1024
     assert abs(parallel.trainable_grad_elems() * 4 / 1e6 - 8.8) < 0.1
+
+
+def _sweep_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_eval_golden import make_case, to_reference_inputs
+    from nafae_b200 import evaluate
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    parallel.init_from_env(backend="gloo")
+    # 90 single-frame "segments": every rank records the detections of its own contiguous shard
+    z = make_case(seed=21, n_imgs=90, n_cls=9)
+    recs, dets, class_list = to_reference_inputs(z)
+    begin, end = parallel.shard_segments(90, rank, world)
+    mine = [k for k, img in enumerate(dets[0]) if begin <= img < end]
+    local = [[lst[k] for k in mine] for lst in dets]
+    merged = parallel.gather_dets(local)
+    whole = evaluate.box_accuracy_details(recs, dets, class_list)
+    got = evaluate.box_accuracy_details(recs, merged, class_list)
+    out[rank] = bool(merged[0] == dets[0] and merged[1] == dets[1] and
+                     np.array_equal(got["class_match_count"], whole["class_match_count"]) and
+                     got["macro"] == whole["macro"] and
+                     evaluate.phrase_accuracy_details(recs, merged, class_list)["macro"] ==
+                     evaluate.phrase_accuracy_details(recs, dets, class_list)["macro"])
+    dist.destroy_process_group()
+
+
+def test_sharded_inference_sweep_merges_to_the_single_process_result_gloo_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sweep_worker, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
