@@ -461,7 +461,9 @@ def run_ours(args):
                                           % (buckets[0].num_ctas, buckets[0].cta_threads),
                                           parallel.trainable_grad_elems(), parallel.trainable_grad_elems() * 4 / 1e6,
                                           comm_sms))
-        line["gpu_launches"] = K * (steps[0].kernels_per_step() + (0 if args.nccl_allreduce else 1))
+        # + the all-reduce kernel (ours unless NCCL) + the one-warp gate kernel in front of it
+        line["gpu_launches"] = K * (steps[0].kernels_per_step() + (0 if args.nccl_allreduce else 1) +
+                                    (1 if pipelined and not args.no_gate else 0))
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
