@@ -766,7 +766,9 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 // dL/dS_ has at most one non-zero per (frame, column) -- the argmax box -- so every sweep is a
 // gather-scale-accumulate over <= F*NQ pairs, not a GEMM.  All cross-CTA inputs are staged into
 // shared memory with one round of independent loads; gather loops issue loads in batches.
-__global__ void __launch_bounds__(kBwdThreads, 1) ground_bwd_kernel(const BwdParams p) {
+// min 2 CTAs/SM: caps the kernel at 64 registers (66 without the bound = ONE 512-thread CTA per SM by
+// registers, i.e. 16 resident CTAs on the 16 SMs the pipelined step leaves to the head: 15 waves)
+__global__ void __launch_bounds__(kBwdThreads, 2) ground_bwd_kernel(const BwdParams p) {
   NAFAE_CTA_TRACE(cta_trace, 4);
   extern __shared__ __align__(16) float sm[];
   __shared__ int s_nlive;
