@@ -438,7 +438,7 @@ def run_ours(args):
                 gpu_launches=K * steps[0].kernels_per_step(),
                 roofline=dict(bound="hbm", kernel="align_pool_fwd_slab", achieved=achieved, peak=peak,
                               unit="GB/s", frac=achieved / peak, traffic=traffic,
-                              kernel_us=kern_us, kernel_grid_sms=int(torch.cuda.get_device_properties(dev).multi_processor_count) - reserve,
+                              kernel_us=kern_us, kernel_grid_sms=int(_C.lib.nafae_roi_align_persistent_ctas(steps[0].F * (c["C"] // 8))),
                               algorithmic_bytes=ab["total"], peak_source=peak_src,
                               step_frac=(ab["total"] / (ms_total / K * 1e-3) / 1e9) / peak),
                 clocks=clocks)

@@ -127,6 +127,10 @@ int ROIAlignBackwardLaucher(const float* top_diff, const float spatial_scale, co
  * ONCE by the caller and then left to the library, private to one stream: the residency gate of
  * nafae_gate_wait (below). */
 size_t nafae_roi_align_workspace_bytes(int batch_size, int num_rois);
+/* CTAs the persistent RoIAlign kernel launches for `num_units` (frame, 8-channel-group) work units
+ * under the current nafae_set_reserved_sms setting: the smallest grid whose busiest CTA has no more
+ * units than with every available SM (reporting / capacity planning; no launch). */
+int nafae_roi_align_persistent_ctas(int num_units);
 int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size,
                             int num_rois, int height, int width, int channels, int out_height,
                             int out_width, int pool_mode, const float* bottom_rois, float* top_data,

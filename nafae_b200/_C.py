@@ -38,6 +38,7 @@ SIGNATURES = {
     "ROIAlignBackwardLaucher": (c_int, [c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
                                         c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "nafae_roi_align_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "nafae_roi_align_persistent_ctas": (c_int, [c_int]),
     "nafae_roi_align_forward": (c_int, [c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
                                         c_int, c_int, c_int, c_void_p, c_void_p, c_uint, c_void_p,
                                         c_size_t, c_void_p]),

@@ -616,6 +616,18 @@ int smem_optin_limit() {
   return cached;
 }
 
+// Persistent grid for `units` equal work units: the units are split statically, so the kernel ends
+// when the CTAs with ceil(units / grid) units end -- use the SMALLEST grid with that same maximum
+// (2560 units on 132 SMs: 20 per CTA either way, but 128 CTAs instead of 132) and leave the other
+// SMs to whatever runs concurrently.
+int slab_grid(int units) {
+  int grid = persistent_grid();
+  if (grid > units) grid = units;
+  if (grid < 1) return 1;
+  const int per_cta = (units + grid - 1) / grid;
+  return (units + per_cta - 1) / per_cta;
+}
+
 template <int W_CT, int HWP_CT, int CPL>
 int launch_slab(const SlabParams& p, int pool, size_t smem, cudaStream_t stream) {
   auto kern = pool == NAFAE_POOL_AVG ? align_pool_fwd_slab<NAFAE_POOL_AVG, W_CT, HWP_CT, CPL>
@@ -625,8 +637,7 @@ int launch_slab(const SlabParams& p, int pool, size_t smem, cudaStream_t stream)
     set_error("roi_align: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     return -(int)e;
   }
-  int grid = persistent_grid();
-  if (grid > p.units) grid = p.units;
+  const int grid = slab_grid(p.units);
   kern<<<grid, kSlabThreads, smem, stream>>>(p);
   return launch_status("align_pool_fwd_slab");
 }
@@ -700,6 +711,8 @@ int grid_for(long long total) {
 using namespace nafae;
 
 NAFAE_CTA_TRACE_READER(nafae_debug_cta_trace_roi_align)
+
+NAFAE_API int nafae_roi_align_persistent_ctas(int num_units) { return slab_grid(num_units); }
 
 NAFAE_API size_t nafae_roi_align_workspace_bytes(int batch_size, int num_rois) {
   (void)batch_size;
