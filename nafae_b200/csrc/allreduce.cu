@@ -204,34 +204,45 @@ __global__ void __launch_bounds__(kArThreads, 1024 / kArThreads) allreduce_avg_k
 // carry the traffic, one phase and one cross-GPU barrier disappear, and there is no gather pass
 // re-reading the reduced slices.
 constexpr int kTmaThreads = 256;
-constexpr int kTmaStages = 4;             // chunks in the peer-data ring: three in flight per CTA
 constexpr int kTmaRingBytes = 128 * 1024;
 
-template <int W>
+// V = 0: the configuration measured in round 1 (4-slot ring of 128 KB, one thread issues every bulk
+//        copy).  At world 8 that is 4 KB chunks: 17 iterations x 15 bulk copies per CTA.
+// V = 1: experiment for larger worlds (NAFAE_AR_VARIANT=1; not yet on hardware): 3-slot ring with
+//        twice the chunk size at W = 8 / 4 (half the iterations and barriers per CTA), and lane q of
+//        warp 0 issues the copies that involve peer (rank + q) % world, so the 15 copies of a chunk
+//        leave in parallel instead of one after the other.
+template <int W, int V>
 struct TmaCfg {  // W = compile-time bound on the world size
+  static constexpr int kStages = V == 0 ? 4 : 3;
   // per peer per stage, a multiple of 4 KB (16 bytes per thread per pass of the 256 threads)
-  static constexpr int kChunkBytes = kTmaRingBytes / (kTmaStages * (W - 1)) / 4096 * 4096;
+  static constexpr int kChunkBytes =
+      V == 0 ? kTmaRingBytes / (kStages * (W - 1)) / 4096 * 4096 : (W == 8 ? 8192 : W == 4 ? 16384 : 32768);
   static constexpr int kChunk4 = kChunkBytes / 16;
   static constexpr int kOwn = kChunk4 / kTmaThreads;  // float4 of the own copy per thread
-  static constexpr size_t kRing = (size_t)kTmaStages * (W - 1) * kChunkBytes;
+  static constexpr size_t kRing = (size_t)kStages * (W - 1) * kChunkBytes;
   static constexpr size_t kSmem = kRing + 2 * (size_t)kChunkBytes;
+  static_assert(kSmem <= 200 * 1024 && kOwn >= 1, "all-reduce ring does not fit");
 };
 
-template <int W>
+template <int W, int V>
 __global__ void __launch_bounds__(kTmaThreads, 1) allreduce_tma_kernel(const ArParams p) {
   NAFAE_CTA_TRACE(cta_trace, 5);
-  constexpr int kChunk4 = TmaCfg<W>::kChunk4;
-  constexpr int kOwn = TmaCfg<W>::kOwn;
+  using Cfg = TmaCfg<W, V>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kChunk4 = Cfg::kChunk4;
+  constexpr int kOwn = Cfg::kOwn;
   extern __shared__ __align__(128) unsigned char ar_smem[];
-  float4* in = reinterpret_cast<float4*>(ar_smem);                          // [stage][W-1][kChunk4]
-  float4* out = reinterpret_cast<float4*>(ar_smem + TmaCfg<W>::kRing);      // [2][kChunk4]
-  __shared__ __align__(8) uint64_t full[kTmaStages];
+  float4* in = reinterpret_cast<float4*>(ar_smem);                    // [stage][W-1][kChunk4]
+  float4* out = reinterpret_cast<float4*>(ar_smem + Cfg::kRing);      // [2][kChunk4]
+  __shared__ __align__(8) uint64_t full[kStages];
 
   char* mine = p.bufs[p.rank];
   unsigned* epoch_word = reinterpret_cast<unsigned*>(mine + kArFlagsBytes);
   int* finished = reinterpret_cast<int*>(mine + kArFlagsBytes + 64);
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(epoch_word) + 1u;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool issuer = V == 0 ? tid == 0 : tid < p.world;  // threads that own bulk-copy groups
   const long long n4 = p.count >> 2;
   const long long slice4 = n4 / p.world;
   const long long per_cta = (slice4 + gridDim.x - 1) / gridDim.x;
@@ -243,33 +254,43 @@ __global__ void __launch_bounds__(kTmaThreads, 1) allreduce_tma_kernel(const ArP
   const float4* own = reinterpret_cast<const float4*>(mine + kArHeaderBytes) + base4 + c_begin;
 
   if (tid == 0) {
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
   cta_barrier_all_ranks(p, 0, epoch);  // includes __syncthreads on both sides
 
   auto chunk_len4 = [&](int i) { return (int)min((long long)kChunk4, c_end - (c_begin + (long long)i * kChunk4)); };
-  auto issue_loads = [&](int i) {  // thread 0: the peers' copies of chunk i -> ring slot i % stages
-    const int s = i % kTmaStages;
+  // the peers' copies of chunk i -> ring slot i % stages.  V = 0: thread 0 alone; V = 1: all of warp 0
+  // calls this (lane 0 arms the barrier, lane q >= 1 pulls from peer (rank + q) % world)
+  auto issue_loads = [&](int i) {
+    const int s = i % kStages;
     const uint32_t bytes = (uint32_t)chunk_len4(i) * 16u;
     const long long off4 = base4 + c_begin + (long long)i * kChunk4;
-    mbar_arrive_expect_tx(&full[s], bytes * (uint32_t)(p.world - 1));
-    for (int q = 1; q < p.world; ++q) {
+    auto pull = [&](int q) {
       const int r = (p.rank + q) % p.world;  // start at different peers to spread the links
       const int slot = r < p.rank ? r : r - 1;
       bulk_g2s(in + ((size_t)s * (W - 1) + slot) * kChunk4,
                reinterpret_cast<const float4*>(p.bufs[r] + kArHeaderBytes) + off4, bytes, &full[s]);
+    };
+    if (V == 0) {
+      mbar_arrive_expect_tx(&full[s], bytes * (uint32_t)(p.world - 1));
+      for (int q = 1; q < p.world; ++q) pull(q);
+    } else {
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], bytes * (uint32_t)(p.world - 1));
+      __syncwarp();
+      if (lane >= 1 && lane < p.world) pull(lane);
     }
   };
-  if (tid == 0) {
+  const bool loader = V == 0 ? tid == 0 : tid < 32;  // who calls issue_loads (warp-uniform for V = 1)
+  if (loader) {
     asm volatile("fence.proxy.async;" ::: "memory");
-    for (int i = 0; i < kTmaStages - 1 && i < nchunks; ++i) issue_loads(i);
+    for (int i = 0; i < kStages - 1 && i < nchunks; ++i) issue_loads(i);
   }
   for (int i = 0; i < nchunks; ++i) {
-    const int s = i % kTmaStages, so = i & 1;
+    const int s = i % kStages, so = i & 1;
     const int len4 = chunk_len4(i);
     // slot of chunk i-1 is free since the closing __syncthreads of the previous iteration
-    if (tid == 0 && i + kTmaStages - 1 < nchunks) issue_loads(i + kTmaStages - 1);
+    if (loader && i + kStages - 1 < nchunks) issue_loads(i + kStages - 1);
     // own copy -> registers, in flight while the peers' data arrives
     float4 mine4[kOwn];
 #pragma unroll
@@ -277,9 +298,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) allreduce_tma_kernel(const ArP
       const int k = tid + j * kTmaThreads;
       mine4[j] = k < len4 ? own[(size_t)i * kChunk4 + k] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    mbar_wait(&full[s], (uint32_t)(i / kTmaStages) & 1u);
+    mbar_wait(&full[s], (uint32_t)(i / kStages) & 1u);
     // the bulk stores that read out[so] two chunks ago must have drained it
-    if (tid == 0 && i >= 2) bulk_wait_read<1>();
+    if (issuer && i >= 2) bulk_wait_read<1>();
     __syncthreads();
     const float4* src = in + (size_t)s * (W - 1) * kChunk4;
     float4* dst = out + (size_t)so * kChunk4;
@@ -310,16 +331,21 @@ __global__ void __launch_bounds__(kTmaThreads, 1) allreduce_tma_kernel(const ArP
     }
     fence_proxy_async_smem();  // generic-proxy writes of out[so] -> visible to the bulk-copy engine
     __syncthreads();           // ... and everybody is done reading ring slot s
-    if (tid == 0) {
+    if (issuer) {
       const long long off4 = base4 + c_begin + (long long)i * kChunk4;
-      for (int q = 0; q < p.world; ++q) {
-        const int r = (p.rank + q) % p.world;  // own copy first, then spread over the links
+      if (V == 0) {
+        for (int q = 0; q < p.world; ++q) {
+          const int r = (p.rank + q) % p.world;  // own copy first, then spread over the links
+          bulk_s2g(reinterpret_cast<float4*>(p.bufs[r] + kArHeaderBytes) + off4, dst, (uint32_t)len4 * 16u);
+        }
+      } else {  // thread q pushes to rank (rank + q) % world; every issuer owns its own bulk groups
+        const int r = (p.rank + tid) % p.world;
         bulk_s2g(reinterpret_cast<float4*>(p.bufs[r] + kArHeaderBytes) + off4, dst, (uint32_t)len4 * 16u);
       }
       bulk_commit();
     }
   }
-  if (tid == 0) {
+  if (issuer) {
     bulk_wait_all<0>();  // every push has been performed
     asm volatile("fence.proxy.async;" ::: "memory");
   }
@@ -334,10 +360,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) allreduce_tma_kernel(const ArP
   }
 }
 
-template <int W>
+template <int W, int V>
 int launch_tma(const ArParams& p, int num_ctas, cudaStream_t stream) {
-  const size_t smem = TmaCfg<W>::kSmem;
-  auto kern = allreduce_tma_kernel<W>;
+  const size_t smem = TmaCfg<W, V>::kSmem;
+  auto kern = allreduce_tma_kernel<W, V>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("allreduce: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
@@ -428,9 +454,15 @@ NAFAE_API int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t
     // hardware -- NAFAE_AR_FORCE_W=4 selects it (dev/test).
     int width = world == 2 ? 2 : 8;
     if (const char* f = getenv("NAFAE_AR_FORCE_W")) width = atoi(f) >= world ? atoi(f) : width;
-    if (width == 2) return launch_tma<2>(p, num_ctas, stream);
-    if (width <= 4) return launch_tma<4>(p, num_ctas, stream);
-    return launch_tma<8>(p, num_ctas, stream);
+    const char* v = getenv("NAFAE_AR_VARIANT");
+    if (v != nullptr && atoi(v) == 1) {  // experiment, see TmaCfg
+      if (width == 2) return launch_tma<2, 1>(p, num_ctas, stream);
+      if (width <= 4) return launch_tma<4, 1>(p, num_ctas, stream);
+      return launch_tma<8, 1>(p, num_ctas, stream);
+    }
+    if (width == 2) return launch_tma<2, 0>(p, num_ctas, stream);
+    if (width <= 4) return launch_tma<4, 0>(p, num_ctas, stream);
+    return launch_tma<8, 0>(p, num_ctas, stream);
   }
   if (cta_threads == 128)
     allreduce_avg_kernel<128><<<num_ctas, 128, 0, stream>>>(p);

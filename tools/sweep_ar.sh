@@ -2,9 +2,10 @@
 # usage: sweep_ar.sh NGPU  -- all-reduce variants standalone and inside the pipelined step (dev tool)
 N=$1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541"
-for cfg in "0 8" "0 16" "0 32"; do
+for cfg in "0 16" "0 32"; do
   set -- $cfg
   NAFAE_AR_THREADS=$1 NAFAE_AR_CTAS=$2 timeout 100 $TR tools/test_allreduce.py 2>&1 | grep -E "^world|rror" | sed "s/^/[threads $1 ctas $2] /"
+  NAFAE_AR_VARIANT=1 NAFAE_AR_THREADS=$1 NAFAE_AR_CTAS=$2 timeout 100 $TR tools/test_allreduce.py 2>&1 | grep -E "^world|rror" | sed "s/^/[variant 1, threads $1 ctas $2] /"
 done
 run() {  # label, env..., -- extra bench args
   label=$1; shift
@@ -21,5 +22,6 @@ except Exception as e:
 PY
 }
 run "tma x16 on 16 SMs, gated" NAFAE_AR_THREADS=0 --
+run "tma x16 variant 1 (3 slots, 2x chunks, parallel issue)" NAFAE_AR_THREADS=0 NAFAE_AR_VARIANT=1 --
 run "tma x12 on 12 SMs, gated" NAFAE_AR_THREADS=0 NAFAE_COMM_SMS=12 --
 run "tma x8 on 8 SMs, gated" NAFAE_AR_THREADS=0 NAFAE_COMM_SMS=8 --
