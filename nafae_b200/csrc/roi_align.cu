@@ -288,7 +288,7 @@ __device__ __forceinline__ void cons_barrier() {  // the 16 consumer warps only
   asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory");
 }
 
-template <int POOL, int W_CT, int HWP_CT, int CPL>
+template <int POOL, int W_CT, int HWP_CT, int CPL, int NBLK_CT>
 __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const SlabParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: [stages][cg][hwp] floats | RoiEntry[kMaxRoiTable] | int roi_id[kMaxRoiTable] | bars |
@@ -483,7 +483,9 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
   }
 
   int cur_f = -1, cur_start = -1;  // which (frame, chunk start) the table holds
-  const int nblk = p.cg / (4 * CPL);  // channel blocks per RoI inside a unit
+  // channel blocks per RoI inside a unit (compile-time for the two production shapes: the
+  // idx / nblk split below is a 20-instruction integer division otherwise)
+  const int nblk = NBLK_CT ? NBLK_CT : p.cg / (4 * CPL);
   const int cq = lane >> 3, pw = lane & 7;
   int g_base = 0;  // running pass-group counter (uniform): deals groups round-robin to warps
   float* my_stage = out_stage + warp * (4 * CPL * kOut * kOut);
@@ -628,10 +630,10 @@ int slab_grid(int units) {
   return (units + per_cta - 1) / per_cta;
 }
 
-template <int W_CT, int HWP_CT, int CPL>
+template <int W_CT, int HWP_CT, int CPL, int NBLK_CT>
 int launch_slab(const SlabParams& p, int pool, size_t smem, cudaStream_t stream) {
-  auto kern = pool == NAFAE_POOL_AVG ? align_pool_fwd_slab<NAFAE_POOL_AVG, W_CT, HWP_CT, CPL>
-                                     : align_pool_fwd_slab<NAFAE_POOL_MAX, W_CT, HWP_CT, CPL>;
+  auto kern = pool == NAFAE_POOL_AVG ? align_pool_fwd_slab<NAFAE_POOL_AVG, W_CT, HWP_CT, CPL, NBLK_CT>
+                                     : align_pool_fwd_slab<NAFAE_POOL_MAX, W_CT, HWP_CT, CPL, NBLK_CT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("roi_align: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
@@ -692,9 +694,9 @@ int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W
   p.units = B * p.groups;
   p.gate = gate;
   const size_t smem = (size_t)cg * hwp * 4 * stages + fixed;
-  if (W == 50 && hwp == 1928) return launch_slab<50, 1928, 2>(p, pool, smem, stream);  // 38x50 maps
-  if (small_map && cg == 32) return launch_slab<14, 200, 4>(p, pool, smem, stream);  // 14x14
-  return launch_slab<0, 0, 2>(p, pool, smem, stream);
+  if (W == 50 && hwp == 1928 && cg == 8) return launch_slab<50, 1928, 2, 1>(p, pool, smem, stream);  // 38x50
+  if (small_map && cg == 32) return launch_slab<14, 200, 4, 2>(p, pool, smem, stream);                // 14x14
+  return launch_slab<0, 0, 2, 0>(p, pool, smem, stream);
 }
 
 int grid_for(long long total) {
