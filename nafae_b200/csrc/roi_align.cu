@@ -250,6 +250,9 @@ constexpr int kS = 8;               // sample grid side
 #ifndef NAFAE_CONS_WARPS
 #define NAFAE_CONS_WARPS 16
 #endif
+#ifndef NAFAE_SLAB_PREDICATED
+#define NAFAE_SLAB_PREDICATED 0
+#endif
 constexpr int kConsWarps = NAFAE_CONS_WARPS;
 constexpr int kConsThreads = kConsWarps * 32;
 constexpr int kSlabThreads = kConsThreads + 32;  // + producer warp
@@ -304,7 +307,11 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
   float* out_stage = reinterpret_cast<float*>(empty + kStagesMax);  // [kConsWarps][4*CPL][7][7]
   __shared__ int s_nroi, s_next, s_warp_cnt[kConsWarps], s_fbeg[kPreFrames + 1];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp index through a lane-0 broadcast: the compiler then knows it is warp-uniform, and loops whose
+  // bounds depend on it need no collective-reconvergence scaffolding (WARPSYNC.COLLECTIVE / VOTE /
+  // ENDCOLLECTIVE, ~3 instructions per shuffle) around the pooling shuffles
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   NAFAE_CTA_TRACE(cta_trace, 1);  // debug builds only
   // contiguous unit range per CTA: it touches 1-2 frames, whose RoI tables are built once
   const int u_begin = (int)((long long)p.units * blockIdx.x / gridDim.x);
@@ -537,6 +544,31 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
         // T0/T1: horizontally interpolated cell rows (hstart, hstart+1) of the current sample row;
         // kept across sample rows while the cell rows repeat or advance by one (warp-uniform tests)
         float s[CPL][kS], T0[CPL], T1[CPL];
+#if NAFAE_SLAB_PREDICATED
+        // experiment (make pred): the same reuse rule as predicated loads + selects instead of
+        // branches -- no reconvergence / collective-shuffle scaffolding in the pass loop, every
+        // instruction slot is spent but a skipped load costs no shared-memory wavefront
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) T0[k] = T1[k] = 0.f;
+#pragma unroll
+        for (int ph = 0; ph < kS; ++ph) {
+          const int d = ph ? hoff[ph] - hoff[ph - 1] : -1;
+          const bool ld_bot = d != 0;                  // the cell rows changed at all
+          const bool ld_top = ld_bot && d != W * 4;    // ... and not just by one row (top = old bottom)
+          const unsigned char* t = lane_base + hoff[ph];
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) {
+            const float* q = reinterpret_cast<const float*>(t + (size_t)k * 4 * hwp * 4);
+            float top = ld_bot ? T1[k] : T0[k];
+            if (ld_top) top = fmaf(q[1], w1, q[0] * w0);
+            float bot = T1[k];
+            if (ld_bot) bot = fmaf(q[W + 1], w1, q[W] * w0);
+            T0[k] = top;
+            T1[k] = bot;
+            s[k][ph] = fmaf(bot, h1[ph], top * h0[ph]);
+          }
+        }
+#else
 #pragma unroll
         for (int ph = 0; ph < kS; ++ph) {
           const int d = ph ? hoff[ph] - hoff[ph - 1] : -1;
@@ -561,6 +593,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
 #pragma unroll
           for (int k = 0; k < CPL; ++k) s[k][ph] = fmaf(T1[k], h1[ph], T0[k] * h0[ph]);
         }
+#endif
         // pooled block -> per-warp staging (channel-major like the output) -> one bulk store
         if (lane == 0) bulk_wait_read<0>();  // the previous pass's store has drained the buffer
         __syncwarp();
