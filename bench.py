@@ -52,7 +52,12 @@ def parse_args():
     ap.add_argument("--gate-head", action="store_true",
                     help="also hold the head branch behind the gate (measured slower)")
     ap.add_argument("--nccl-allreduce", action="store_true",
-                    help="use NCCL for the gradient all-reduce instead of the peer-memory kernel")
+                    help="use NCCL for the gradient all-reduce instead of this package's kernels")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "multicast", "peer"],
+                    help="gradient all-reduce kernel: NVLS multimem (in-switch reduction) when the box supports "
+                         "NVSwitch multicast, else the bulk-copy peer-memory kernel")
+    ap.add_argument("--comm-sms", type=int, default=-1, help="SMs kept free for the all-reduce CTAs")
+    ap.add_argument("--ar-ctas", type=int, default=-1, help="CTAs of the all-reduce kernel")
     return ap.parse_args()
 
 
@@ -237,7 +242,9 @@ def run_ours(args):
         if args.nccl_allreduce:
             buckets = [parallel.GradBucket(parallel.trainable_grad_elems(), dev, world) for _ in range(2)]
         else:
-            buckets = [parallel.PeerAllReduce(parallel.trainable_grad_elems(), dev) for _ in range(2)]
+            kw = dict(num_ctas=args.ar_ctas) if args.ar_ctas > 0 else {}
+            buckets = [parallel.make_allreduce(parallel.trainable_grad_elems(), dev, kind=args.allreduce,
+                                               peer_kw=kw, mc_kw=kw) for _ in range(2)]
         for st, b in zip(steps, buckets):
             st.grad_word = b.views([(st.NQ, c["D"])])[0]
     if world > 1:
@@ -250,8 +257,18 @@ def run_ours(args):
     from nafae_b200.pipeline import capture_pipelined, capture_pipelined_body
     pipelined = not args.no_pipeline
     comm_sms = 0
-    if world > 1 and (args.nccl_allreduce or buckets[0].cta_threads != 128 or not pipelined):
-        comm_sms = parallel.COMM_SMS  # the 128-thread all-reduce CTAs co-reside with the slab CTAs instead
+    ar_kind = None
+    if world > 1:
+        ar_kind = "nccl" if args.nccl_allreduce else buckets[0].kind
+        if args.comm_sms >= 0:
+            comm_sms = args.comm_sms
+        elif ar_kind == "multicast":
+            # 512-thread CTAs without shared memory: two per SM
+            comm_sms = (buckets[0].num_ctas * buckets[0].cta_threads + 1023) // 1024
+        elif ar_kind == "peer" and buckets[0].cta_threads == 128 and pipelined:
+            comm_sms = 0  # the 128-thread all-reduce CTAs co-reside with the slab CTAs instead
+        else:
+            comm_sms = parallel.COMM_SMS
     reserve = args.reserve_sms if args.reserve_sms >= 0 else (HEAD_SMS if pipelined else 0) + comm_sms
     _C.lib.nafae_set_reserved_sms(reserve)
     side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
@@ -328,8 +345,11 @@ def run_ours(args):
                 i += S
         for k in range(i, n):
             graphs[k & 1].replay()
-        if buckets:  # flush: the last step's gradients are still un-reduced
-            allreduce(buckets[(n - 1) & 1])
+        if buckets and n > 0:  # flush: the last step's gradients are still un-reduced
+            # pipelined replay j runs the head of set 1-j (writes buckets[1-j]) and reduces buckets[j];
+            # sequential replay j runs the head of set j and reduces buckets[1-j]
+            last = (n - 1) & 1
+            allreduce(buckets[1 - last] if pipelined else buckets[last])
 
     loop(Wm)
     barrier()
@@ -348,6 +368,13 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     value = world * K * c["Na"] / (ms_total / 1e3)
+    replicas_identical = None
+    if world > 1:
+        # every replica must hold the same averaged gradients after the timed loop + flush
+        chk = torch.stack([b.buf.view(torch.int32).sum(dtype=torch.int64) for b in buckets])
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        replicas_identical = all(bool(torch.equal(allc[0], t)) for t in allc)
 
     # dominant kernel alone, same stream, same alternating inputs (roofline.achieved)
     def align_only(st):
@@ -449,6 +476,17 @@ def run_ours(args):
         % (S, " || gradient all-reduce" if world > 1 else "", reserve)) if pipelined else (
         "sequential: one CUDA graph per step, five kernels back to back")
     if world > 1:
+        line["replicas_identical"] = replicas_identical
+        line["config"]["allreduce_kind"] = ar_kind
+    if world > 1 and ar_kind == "multicast":
+        line["config"]["allreduce"] = (
+            "NVLS all-reduce (AVG) per step over a flat fp32 bucket of %d elems (%.1f MB): allreduce_mc_kernel, "
+            "multimem.ld_reduce in the NVSwitch + multimem.st broadcast, %d CTAs x %d threads, a parallel branch "
+            "of the NEXT step's CUDA graph behind the RoIAlign kernel's residency gate; %d SMs left free for it"
+            % (parallel.trainable_grad_elems(), parallel.trainable_grad_elems() * 4 / 1e6,
+               buckets[0].num_ctas, buckets[0].cta_threads, comm_sms))
+        line["gpu_launches"] = K * (steps[0].kernels_per_step() + 1 + (1 if pipelined and not args.no_gate else 0))
+    elif world > 1:
         line["config"]["allreduce"] = ("%s all-reduce (AVG) per step over a flat fp32 bucket of %d elems (%.1f MB), "
                                        "a parallel branch of the NEXT step's CUDA graph (overlaps its "
                                        "NMS/RoIAlign, launched behind the RoIAlign kernel's residency gate); "

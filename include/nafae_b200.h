@@ -31,7 +31,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t; /* same opaque handle as CUDA driver_types.h */
 #endif
 
-#define NAFAE_B200_ABI_VERSION 2 /* 2: nafae_gate_wait, nafae_allreduce_avg(cta_threads) */
+#define NAFAE_B200_ABI_VERSION 3 /* 3: nafae_allreduce_avg(flags), nafae_gate_sync, nafae_mc_*, nafae_allreduce_mc */
 
 /* pooling applied on top of the sampled RoIAlign grid (modules/roi_align.py:6-42) */
 #define NAFAE_POOL_NONE 0 /* RoIAlign    : output is the aligned_height x aligned_width grid   */
@@ -48,8 +48,8 @@ const char* nafae_last_error(void);
 
 /* Persistent kernels (the RoIAlign slab kernel) launch one CTA per SM.  When a collective runs
  * concurrently on another stream (data-parallel gradient all-reduce), leave `n` SMs free for its
- * CTAs so neither kernel waits for the other's residency.  Process-wide, default 0; returns the
- * previous value.  n is clamped to [0, SMs-1]. */
+ * CTAs so neither kernel waits for the other's residency.  Per CUDA device (the calling thread's
+ * current one), default 0; returns the previous value.  n is clamped to [0, SMs-1]. */
 int nafae_set_reserved_sms(int n);
 
 /* Residency gate for kernels that run CONCURRENTLY with the persistent RoIAlign kernel (the head
@@ -65,6 +65,11 @@ int nafae_set_reserved_sms(int n);
 #define NAFAE_GATE_BYTES 32
 #define NAFAE_ROI_ALIGN_WS_BYTES 64
 int nafae_gate_wait(void* gate, int slot, cudaStream_t stream);
+/* Marks every gated launch enqueued on `stream` so far as seen by every slot: the next
+ * nafae_gate_wait of any slot blocks until the NEXT gated launch opens the gate.  Enqueue it once
+ * after gated launches that had no waiter (warm-up runs), before the paired launches begin --
+ * otherwise each wait would be satisfied by the previous launch's open. */
+int nafae_gate_sync(void* gate, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------- NMS ---- */
 
@@ -177,7 +182,10 @@ int ROIPoolBackwardLaucher(const float* top_diff, const float spatial_scale, con
  *     10*mean(frame_score)  (model.py:606)
  * The workspace carries the saved state from forward to backward and must not be touched in
  * between; it must be ZERO-FILLED ONCE after allocation (the kernels leave their arrival
- * counters zeroed on exit).  grad_margin_loss (1) f32 DEVICE = dL/d(margin_loss).
+ * counters zeroed on exit).  grad_margin_loss (1) f32 DEVICE = dL/d(margin_loss); NULL = the step
+ * wrapper's L1Loss(margin_loss, 0).backward() (model.py:771-772): sign(margin_loss), which the
+ * forward left in the workspace.  entities_length values above Ne select all Ne columns and still
+ * divide by the raw length, like the reference's slicing (model.py:535-538).
  * grad_vis (Na*Ns*Nb, D) and grad_word (Na*Ne, D) are fully written. */
 size_t nafae_ground_workspace_bytes(int Na, int Ns, int Nb, int Ne, int D);
 int nafae_ground_forward(const float* vis_feats, const float* word_feats,
@@ -198,6 +206,21 @@ int nafae_ground_backward(const float* grad_margin_loss, const float* vis_feats,
 int nafae_ground_postprocess(const int64_t* D_ind, const float* D_sim, int Na, int Ns, int Nb,
                              int Ne, int64_t* out_ind, float* out_sim, cudaStream_t stream);
 
+/* ------------------------------------------------------- step wrapper: clip + Adam ---- */
+
+/* Replaces clip_grad_norm_(ground_model.parameters(), args.clip) + optimizer.step() --
+ * model.py:773-774 (Adam, lr 1e-3, weight_decay 1e-5: model.py:1030-1036) -- over ONE flat fp32
+ * buffer of the trainable parameters (the bucket the data-parallel all-reduce averages), two launches,
+ * no host synchronisation.  grad is scaled in place by min(1, max_norm / (||grad||_2 + 1e-6)) like
+ * clip_grad_norm_ (max_norm <= 0 disables clipping), then torch.optim.Adam's update (L2 weight decay
+ * added to the gradient, bias correction by the step count kept in the workspace).  The norm is summed
+ * in a fixed order: replicas that start identical and see the same averaged gradient stay identical.
+ * workspace: nafae_clip_adam_workspace_bytes() bytes, ZERO-FILLED ONCE (holds the step count). */
+size_t nafae_clip_adam_workspace_bytes(void);
+int nafae_clip_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                         float lr, float beta1, float beta2, float eps, float weight_decay,
+                         float max_norm, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* ------------------------------------------------- data-parallel gradient all-reduce ---- */
 
 /* New functionality (the reference is single-GPU: --mGPUs is parsed and never read, model.py:91-99).
@@ -213,7 +236,13 @@ int nafae_ground_postprocess(const int64_t* D_ind, const float* D_sim, int Na, i
  * cta_threads: 0 = bulk-copy kernel (cp.async.bulk pulls the slice from every rank into shared
  * memory, reduces, and pushes the result into every rank's buffer; one CTA per SM, num_ctas = the SMs
  * nafae_set_reserved_sms keeps free); 256 / 128 = per-thread 16-byte loads (four / eight CTAs per
- * SM).  When it overlaps the RoIAlign kernel, enqueue nafae_gate_wait first (see there). */
+ * SM).  flags: NAFAE_AR_VARIANT(v) selects the bulk-copy kernel's ring shape (0 = 4 slots, one
+ * issuing thread; 1 = 3 slots of twice the chunk size, one issuing lane per peer);
+ * NAFAE_AR_WIDTH(w) forces the compile-time world bound (2, 4 or 8, >= world; tests only).
+ * When it overlaps the RoIAlign kernel, enqueue nafae_gate_wait first (see there).
+ * Cross-GPU waits are bounded (2 s): a dead peer sets a sticky error word instead of hanging. */
+#define NAFAE_AR_VARIANT(v) ((unsigned)(v) & 0xfu)
+#define NAFAE_AR_WIDTH(w) (((unsigned)(w) & 0xffu) << 8)
 size_t nafae_ar_buffer_bytes(size_t count_floats, int world);
 size_t nafae_ar_data_offset(void);
 int nafae_ar_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
@@ -221,7 +250,33 @@ int nafae_ar_open(const unsigned char* handle64, void** peer_ptr);
 int nafae_ar_close(void* peer_ptr);
 int nafae_ar_free(void* dev_ptr);
 int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t count_floats, int num_ctas,
-                        int cta_threads, cudaStream_t stream);
+                        int cta_threads, unsigned flags, cudaStream_t stream);
+
+/* NVLS form of the same collective: the bucket lives in memory bound to an NVSwitch MULTICAST object,
+ * the sum is formed INSIDE the switch (multimem.ld_reduce) and the result is replicated to every rank
+ * by one multicast store (multimem.st) -- per rank the SMs move count/world floats each way instead of
+ * (world-1)/world of the bucket twice.  Setup (once, host side, one process per GPU):
+ *   root : nafae_mc_create(world, bytes, &h, &fd)   -> hand `fd` to the other processes (SCM_RIGHTS)
+ *   other: nafae_mc_import(fd, world, bytes, &h)
+ *   all  : nafae_mc_add_device(h); <host barrier>; nafae_mc_bind(h, &uc, &mc); <host barrier>
+ * `uc` = this rank's own copy (zero-filled; gradients go at uc + nafae_ar_data_offset()), `mc` = the
+ * multicast view.  bytes = nafae_mc_buffer_bytes(count, world).  nafae_mc_supported() = 1 when the
+ * current device can do this (CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED); otherwise use the peer-memory
+ * kernel above.  nafae_allreduce_mc launches ONE kernel (graph-capturable, same calling rules as
+ * nafae_allreduce_avg); cta_threads 0 (= 512), 256, 512 or 1024.  One rank reduces each element, so
+ * replicas are bit-identical; the order of the in-switch sum is the hardware's.
+ * nafae_allreduce_mc_error (host-synchronising) reports whether a cross-GPU wait ever timed out. */
+int nafae_mc_supported(void);
+size_t nafae_mc_buffer_bytes(size_t count_floats, int world);
+int nafae_mc_create(int world, size_t bytes, void** handle, int* fd_out);
+int nafae_mc_import(int fd, int world, size_t bytes, void** handle);
+int nafae_mc_add_device(void* handle);
+int nafae_mc_bind(void* handle, void** uc_ptr, void** mc_ptr);
+size_t nafae_mc_size(void* handle);
+int nafae_mc_free(void* handle);
+int nafae_allreduce_mc(void* uc_base, void* mc_base, int rank, int world, size_t count_floats,
+                       int num_ctas, int cta_threads, cudaStream_t stream);
+int nafae_allreduce_mc_error(void* uc_base);
 
 #ifdef __cplusplus
 }

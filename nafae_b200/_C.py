@@ -27,6 +27,7 @@ SIGNATURES = {
     "nafae_last_error": (ctypes.c_char_p, []),
     "nafae_set_reserved_sms": (c_int, [c_int]),
     "nafae_gate_wait": (c_int, [c_void_p, c_int, c_void_p]),
+    "nafae_gate_sync": (c_int, [c_void_p, c_void_p]),
     "nms_cuda_compute": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float]),
     "nafae_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nafae_nms_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
@@ -58,13 +59,26 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nafae_ground_postprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_void_p]),
+    "nafae_clip_adam_workspace_bytes": (c_size_t, []),
+    "nafae_clip_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float,
+                                     c_float, c_float, c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "nafae_ar_buffer_bytes": (c_size_t, [c_size_t, c_int]),
     "nafae_ar_data_offset": (c_size_t, []),
     "nafae_ar_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), c_void_p]),
     "nafae_ar_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "nafae_ar_close": (c_int, [c_void_p]),
     "nafae_ar_free": (c_int, [c_void_p]),
-    "nafae_allreduce_avg": (c_int, [c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_void_p]),
+    "nafae_allreduce_avg": (c_int, [c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_uint, c_void_p]),
+    "nafae_mc_supported": (c_int, []),
+    "nafae_mc_buffer_bytes": (c_size_t, [c_size_t, c_int]),
+    "nafae_mc_create": (c_int, [c_int, c_size_t, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int)]),
+    "nafae_mc_import": (c_int, [c_int, c_int, c_size_t, ctypes.POINTER(c_void_p)]),
+    "nafae_mc_add_device": (c_int, [c_void_p]),
+    "nafae_mc_bind": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
+    "nafae_mc_size": (c_size_t, [c_void_p]),
+    "nafae_mc_free": (c_int, [c_void_p]),
+    "nafae_allreduce_mc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_int, c_int, c_void_p]),
+    "nafae_allreduce_mc_error": (c_int, [c_void_p]),
 }
 
 MISSING = []
@@ -77,7 +91,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-ABI_VERSION = 2  # include/nafae_b200.h NAFAE_B200_ABI_VERSION this host code was written against
+ABI_VERSION = 3  # include/nafae_b200.h NAFAE_B200_ABI_VERSION this host code was written against
 if not MISSING and int(lib.nafae_abi_version()) != ABI_VERSION:
     raise ImportError("%s has ABI version %d, this package needs %d: rebuild it (make -C nafae_b200/csrc)"
                       % (LIB_PATH, int(lib.nafae_abi_version()), ABI_VERSION))

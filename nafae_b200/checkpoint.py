@@ -47,16 +47,17 @@ def load_checkpoint(path, map_location="cpu"):
     return ckpt
 
 
-def load_head(ckpt, vis_ebd, word_ebd, dvsa=None):
+def load_head(ckpt, vis_ebd, word_ebd, dvsa=None, resume=True):
     """Load `vis_ebd.*` / `word_ebd.*` (strictly) and, if given, whatever `DVSA.*` tensors `dvsa`
-    actually has (this package's DVSA has none: the reference's are dead).  Returns the start epoch
-    the reference resumes from (checkpoint epoch + 1, model.py:1042) and the pooling mode or None."""
+    actually has (this package's DVSA has none: the reference's are dead).  Returns (epoch, pooling
+    mode or None): with `resume` (training, model.py:1042) the epoch to CONTINUE from, checkpoint
+    epoch + 1; with `resume=False` (the val / test phases, model.py:1051) the checkpoint's own epoch."""
     parts = split_state_dict(ckpt["model"])
     vis_ebd.load_state_dict(parts["vis_ebd"], strict=True)
     word_ebd.load_state_dict(parts["word_ebd"], strict=True)
     if dvsa is not None:
         dvsa.load_state_dict(parts["DVSA"], strict=False)
-    return int(ckpt["epoch"]) + 1, ckpt.get("pooling_mode")
+    return int(ckpt["epoch"]) + (1 if resume else 0), ckpt.get("pooling_mode")
 
 
 def save_checkpoint(path, session, epoch, vis_ebd, word_ebd, optimizer=None, pooling_mode="align",

@@ -26,7 +26,6 @@
 // gate (nafae_gate_wait): started at the same instant, its CTAs would land on every SM first and
 // keep the 210 KB persistent CTAs out until the whole all-reduce has finished.
 // The kernel has no host-side state (the epoch lives in the buffer): it is CUDA-graph capturable.
-#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -80,7 +79,19 @@ __device__ __forceinline__ void cta_barrier_all_ranks(const ArParams& p, int sta
   if (tid < p.world) st_release_sys(flag_ptr(p.bufs[tid], stage, blockIdx.x, p.rank), epoch);
   if (tid < p.world) {
     const unsigned* f = flag_ptr(p.bufs[p.rank], stage, blockIdx.x, tid);
+    // bounded (2 s): a dead peer must not hang the GPU; the error word is sticky
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
     while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+      if ((++spins & 1023u) == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) t0 = t;
+        if (t - t0 > 2000000000ull) {
+          *reinterpret_cast<unsigned*>(p.bufs[p.rank] + kArFlagsBytes + 128) = 1u;
+          break;
+        }
+      }
     }
   }
   __syncthreads();
@@ -360,6 +371,120 @@ __global__ void __launch_bounds__(kTmaThreads, 1) allreduce_tma_kernel(const ArP
   }
 }
 
+// ------------------------------------------------------------- NVLS (multimem) variant ----
+// The bucket lives in memory bound to an NVSwitch multicast object (csrc/symm.cu): `mc` is the
+// multicast address of the same offsets `uc` addresses in this rank's own copy.
+//   barrier 0   every rank's bucket is complete (multimem.red +1 on a counter replicated into
+//               every rank's header, each rank spins on its LOCAL copy)
+//   data        rank r owns slice r: multimem.ld_reduce returns the sum of all ranks' copies,
+//               added INSIDE the switch; scale by 1/world; multimem.st replicates the result into
+//               every rank's bucket.  One reducer per element => replicas are bit-identical.
+//   barrier 2   every slice has landed everywhere / nobody still reads my input
+// Per rank the SMs move count/world floats in and out (1.1 MB each way for the 8.8 MB bucket at
+// world 8) instead of pulling and pushing 7/8 of the bucket, so a handful of small CTAs saturate
+// the collective and the ring of shared-memory staging buffers disappears.
+// Barrier counters are monotonic (launch e waits for e*world arrivals): nothing to reset, and a
+// rank that runs ahead can only over-satisfy a slower rank's wait.  Spins are bounded (2 s): a
+// dead peer sets the error word instead of hanging the GPU.
+struct McParams {
+  char* uc;  // this rank's own copy (header + bucket)
+  char* mc;  // multicast view of the same offsets on every rank
+  int rank, world;
+  long long count;  // floats
+};
+
+__device__ __forceinline__ float4 mm_ld_reduce_f4(const void* mc_addr) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc_addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st_f4(void* mc_addr, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void mm_red_release_add(void* mc_addr, unsigned v) {
+  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ar_global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) allreduce_mc_kernel(const McParams p) {
+  NAFAE_CTA_TRACE(cta_trace, 5);
+  constexpr int kU = 8;  // 16-byte multimem loads in flight per thread
+  unsigned* epoch_word = reinterpret_cast<unsigned*>(p.uc + kArFlagsBytes);
+  int* finished = reinterpret_cast<int*>(p.uc + kArFlagsBytes + 64);
+  unsigned* err_word = reinterpret_cast<unsigned*>(p.uc + kArFlagsBytes + 128);
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(epoch_word) + 1u;
+  const unsigned target = epoch * (unsigned)p.world;
+  const int tid = threadIdx.x;
+  const long long n4 = p.count >> 2;
+  const long long slice4 = n4 / p.world;
+  const long long per_cta = (slice4 + gridDim.x - 1) / gridDim.x;
+  const long long c_begin = min(slice4, (long long)blockIdx.x * per_cta);
+  const long long c_end = min(slice4, c_begin + per_cta);
+  const float scale = 1.f / (float)p.world;
+
+  auto barrier_all_ranks = [&](int stage) {
+    __syncthreads();
+    if (tid == 0) {
+      const size_t off = ((size_t)stage * kArMaxCtas + blockIdx.x) * sizeof(unsigned);
+      mm_red_release_add(p.mc + off, 1u);
+      const unsigned* f = reinterpret_cast<const unsigned*>(p.uc + off);
+      const unsigned long long t0 = ar_global_ns();
+      while ((int)(ld_acquire_sys(f) - target) < 0) {
+        if (ar_global_ns() - t0 > 2000000000ull) {
+          *err_word = 1u;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+  };
+
+  barrier_all_ranks(0);
+
+  {
+    char* data = p.mc + kArHeaderBytes + ((size_t)p.rank * (size_t)slice4) * sizeof(float4);
+    for (long long i0 = c_begin; i0 < c_end; i0 += (long long)kU * kThreads) {
+      float4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const long long i = i0 + u * kThreads + tid;
+        if (i < c_end) v[u] = mm_ld_reduce_f4(data + (size_t)i * sizeof(float4));
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const long long i = i0 + u * kThreads + tid;
+        if (i < c_end) {
+          v[u].x *= scale;
+          v[u].y *= scale;
+          v[u].z *= scale;
+          v[u].w *= scale;
+          mm_st_f4(data + (size_t)i * sizeof(float4), v[u]);
+        }
+      }
+    }
+  }
+  __threadfence_system();  // my multicast stores are performed everywhere before I arrive
+  barrier_all_ranks(2);
+
+  __shared__ int s_ticket;
+  if (tid == 0) s_ticket = atomicAdd(finished, 1);
+  __syncthreads();
+  if (s_ticket == (int)gridDim.x - 1 && tid == 0) {
+    *finished = 0;
+    *epoch_word = epoch;
+  }
+}
+
 template <int W, int V>
 int launch_tma(const ArParams& p, int num_ctas, cudaStream_t stream) {
   const size_t smem = TmaCfg<W, V>::kSmem;
@@ -431,7 +556,7 @@ NAFAE_API int nafae_ar_close(void* peer_ptr) {
 NAFAE_API int nafae_ar_free(void* dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? 1 : 0; }
 
 NAFAE_API int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t count_floats,
-                                  int num_ctas, int cta_threads, cudaStream_t stream) {
+                                  int num_ctas, int cta_threads, unsigned flags, cudaStream_t stream) {
   NAFAE_REQUIRE(cta_threads == 0 || cta_threads == 128 || cta_threads == 256,
                 "allreduce: cta_threads must be 0 (bulk-copy kernel), 128 or 256");
   NAFAE_REQUIRE(bufs && world >= 1 && world <= kArMaxWorld && rank >= 0 && rank < world,
@@ -449,19 +574,25 @@ NAFAE_API int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t
   p.count = (long long)count_floats;
   static_assert(kArThreadsMax == 256, "flag layout");
   if (cta_threads == 0) {
-    // template bound on the world size.  Measured on B200 boxes: <2> at world 2, <8> at world 8;
-    // worlds 3..7 run the <8> instantiation (same code, smaller chunks) until <4> has been on
-    // hardware -- NAFAE_AR_FORCE_W=4 selects it (dev/test).
-    int width = world == 2 ? 2 : 8;
-    if (const char* f = getenv("NAFAE_AR_FORCE_W")) width = atoi(f) >= world ? atoi(f) : width;
-    const char* v = getenv("NAFAE_AR_VARIANT");
-    if (v != nullptr && atoi(v) == 1) {  // experiment, see TmaCfg
+    // template bound on the world size: the smallest instantiation that holds `world` (larger
+    // chunks per peer); NAFAE_AR_WIDTH(w) in `flags` forces a wider one (tests run <4> and <8>
+    // on a 2-GPU box that way)
+    int width = world == 2 ? 2 : (world <= 4 ? 4 : 8);
+    const int forced = (int)((flags >> 8) & 0xffu);
+    if (forced != 0) {
+      NAFAE_REQUIRE((forced == 2 || forced == 4 || forced == 8) && forced >= world,
+                    "allreduce: forced width %d invalid for world %d", forced, world);
+      width = forced;
+    }
+    const int variant = (int)(flags & 0xfu);
+    NAFAE_REQUIRE(variant == 0 || variant == 1, "allreduce: unknown variant %d", variant);
+    if (variant == 1) {  // 3-slot ring, larger chunks, parallel issue (see TmaCfg)
       if (width == 2) return launch_tma<2, 1>(p, num_ctas, stream);
-      if (width <= 4) return launch_tma<4, 1>(p, num_ctas, stream);
+      if (width == 4) return launch_tma<4, 1>(p, num_ctas, stream);
       return launch_tma<8, 1>(p, num_ctas, stream);
     }
     if (width == 2) return launch_tma<2, 0>(p, num_ctas, stream);
-    if (width <= 4) return launch_tma<4, 0>(p, num_ctas, stream);
+    if (width == 4) return launch_tma<4, 0>(p, num_ctas, stream);
     return launch_tma<8, 0>(p, num_ctas, stream);
   }
   if (cta_threads == 128)
@@ -469,4 +600,51 @@ NAFAE_API int nafae_allreduce_avg(void* const* bufs, int rank, int world, size_t
   else
     allreduce_avg_kernel<256><<<num_ctas, 256, 0, stream>>>(p);
   return launch_status("allreduce_avg_kernel");
+}
+
+// ------------------------------------------------------------- NVLS (multimem) variant ----
+NAFAE_API size_t nafae_mc_buffer_bytes(size_t count_floats, int world) {
+  return nafae_ar_buffer_bytes(count_floats, world);
+}
+
+NAFAE_API int nafae_allreduce_mc(void* uc_base, void* mc_base, int rank, int world,
+                                 size_t count_floats, int num_ctas, int cta_threads,
+                                 cudaStream_t stream) {
+  NAFAE_REQUIRE(uc_base && mc_base, "allreduce_mc: NULL buffer");
+  NAFAE_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "allreduce_mc: bad rank/world");
+  NAFAE_REQUIRE(num_ctas >= 1 && num_ctas <= kArMaxCtas, "allreduce_mc: num_ctas must be in [1, %d]",
+                kArMaxCtas);
+  NAFAE_REQUIRE(count_floats % ((size_t)4 * world) == 0,
+                "allreduce_mc: count must be a multiple of 4*world (use nafae_mc_buffer_bytes)");
+  if (world == 1 || count_floats == 0) return 1;
+  McParams p;
+  p.uc = static_cast<char*>(uc_base);
+  p.mc = static_cast<char*>(mc_base);
+  p.rank = rank;
+  p.world = world;
+  p.count = (long long)count_floats;
+  if (cta_threads == 0) cta_threads = 512;
+  if (cta_threads == 256)
+    allreduce_mc_kernel<256><<<num_ctas, 256, 0, stream>>>(p);
+  else if (cta_threads == 512)
+    allreduce_mc_kernel<512><<<num_ctas, 512, 0, stream>>>(p);
+  else if (cta_threads == 1024)
+    allreduce_mc_kernel<1024><<<num_ctas, 1024, 0, stream>>>(p);
+  else
+    NAFAE_REQUIRE(false, "allreduce_mc: cta_threads must be 0, 256, 512 or 1024");
+  return launch_status("allreduce_mc_kernel");
+}
+
+// Host-synchronising check (tests, teardown): 0 = no cross-GPU barrier of this buffer ever timed
+// out, 1 = one did (the results of that launch are undefined), <0 = CUDA error.
+NAFAE_API int nafae_allreduce_mc_error(void* uc_base) {
+  NAFAE_REQUIRE(uc_base, "allreduce_mc_error: NULL buffer");
+  unsigned v = 0;
+  cudaError_t e = cudaMemcpy(&v, static_cast<char*>(uc_base) + kArFlagsBytes + 128, sizeof(v),
+                             cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    set_error("allreduce_mc_error: %s", cudaGetErrorString(e));
+    return -(int)e;
+  }
+  return v ? 1 : 0;
 }

@@ -512,8 +512,11 @@ __device__ void phase2_segment(const FwdParams& p, const Ws& w, int a) {
   for (int i = tid; i < d.Ns * d.Na; i += kFwdThreads) {
     const int s = i / d.Na, a2 = i % d.Na;
     const int len = a2 < 256 ? s_len[a2] : __ldg(p.lens + a2);
+    // columns saturate at Ne like the reference's mask slicing (model.py:535-536); only the
+    // divisor uses the raw length (model.py:538)
+    const int ncol = min(len, d.Ne);
     float acc = 0.f;
-    for (int e = 0; e < len; ++e) {
+    for (int e = 0; e < ncol; ++e) {
       const int c = a2 * d.Ne + e;
       const float x = Sblk[s * d.NQ + c];
       acc += x * ((x - c_mn[c]) * c_iden[c]);
@@ -523,7 +526,7 @@ __device__ void phase2_segment(const FwdParams& p, const Ws& w, int a) {
   if (!p.train) return;
 
   // clustering loss of segment a (model.py:553-577)
-  const int len = a < 256 ? s_len[a] : __ldg(p.lens + a);
+  const int len = min(a < 256 ? s_len[a] : __ldg(p.lens + a), d.Ne);
   const int pairs = d.Ns * (d.Ns - 1) / 2;
   float gsum = 0.f;
   int gcnt = 0;
@@ -690,6 +693,9 @@ __device__ void phase3_final(const FwdParams& p, const Ws& w) {
     w.scal[0] = vis_loss;
     w.scal[1] = dem;
     w.scal[2] = mean_fs;
+    // d|loss|/dloss for the L1Loss(margin_loss, 0) of the step wrapper (model.py:771): the backward
+    // uses it when the caller passes no upstream gradient
+    w.scal[3] = loss > 0.f ? 1.f : (loss < 0.f ? -1.f : loss);
     *p.loss = loss;
   }
 }
@@ -779,7 +785,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) ground_bwd_kernel(const BwdPar
   int* flag = w.done_cnt + 1;      // frame-0 rows written
   int* finished = w.done_cnt + 2;  // CTAs that are done (the last one resets the scratch words)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float gout = __ldg(p.gout);
+  const float gout = p.gout != nullptr ? __ldg(p.gout) : __ldcg(w.scal + 3);
   const int bid = blockIdx.x;
 
   if (bid < d.F) {
@@ -1101,8 +1107,7 @@ NAFAE_API int nafae_ground_backward(const float* grad_margin_loss, const float* 
   Dims d;
   NAFAE_REQUIRE(make_dims(Na, Ns, Nb, Ne, D, &d), "ground: sizes must be positive");
   if (check_ground_args(d, workspace, workspace_bytes, 1) != 1) return 0;
-  NAFAE_REQUIRE(grad_margin_loss && vis_feats && word_feats && entities_length && D_ind && D_sim &&
-                    grad_vis && grad_word,
+  NAFAE_REQUIRE(vis_feats && word_feats && entities_length && D_ind && D_sim && grad_vis && grad_word,
                 "ground: NULL buffer");
   BwdParams p;
   p.gout = grad_margin_loss;

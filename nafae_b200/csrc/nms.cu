@@ -24,6 +24,8 @@
 // __f*_rn intrinsics so this file's own compilation cannot re-associate it.  A cheap two-sided
 // filter decides almost every pair without the division; only pairs within 2^-20 of the
 // threshold take the exact division, so the decision is always the reference's.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace nafae {
@@ -323,6 +325,7 @@ struct ScratchCache {
   int device = -1;
 };
 ScratchCache g_nms_scratch;
+std::mutex g_nms_scratch_mu;  // nms_cuda_compute may be called from several host threads
 
 }  // namespace
 }  // namespace nafae
@@ -374,6 +377,7 @@ NAFAE_API void nms_cuda_compute(int* keep_out, int* num_out, float* boxes_host, 
   int dev = 0;
   cudaGetDevice(&dev);
   const size_t need = nafae_nms_workspace_bytes(1, boxes_num);
+  std::lock_guard<std::mutex> lock(g_nms_scratch_mu);  // held across the launch: it uses the scratch
   ScratchCache& sc = g_nms_scratch;
   if (need > 0 && (sc.device != dev || sc.bytes < need)) {
     if (sc.ptr) {

@@ -1,6 +1,8 @@
 // Error reporting and small host-side utilities shared by the entry points.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace nafae {
@@ -34,10 +36,17 @@ int sm_count() {
   return cached[dev];
 }
 
-static int g_reserved_sms = 0;
+// per device (one process may drive several GPUs); relaxed atomics: a plain configuration value
+static std::atomic<int> g_reserved_sms[64];
+
+static int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return dev;
+}
 
 int persistent_grid() {
-  int n = sm_count() - g_reserved_sms;
+  int n = sm_count() - g_reserved_sms[current_device_slot()].load(std::memory_order_relaxed);
   return n < 1 ? 1 : n;
 }
 
@@ -59,6 +68,11 @@ __global__ void gate_open_kernel(int* gate) {  // paths that do not run the pers
   if (threadIdx.x == 0) atomicAdd(gate + 1, 1);
 }
 
+// every slot has "seen" every launch so far: the next wait of any slot blocks until the NEXT open
+__global__ void gate_sync_kernel(int* gate) {
+  if (threadIdx.x < 6) gate[2 + threadIdx.x] = gate[1];
+}
+
 void gate_open(void* gate, cudaStream_t stream) {
   gate_open_kernel<<<1, 32, 0, stream>>>(static_cast<int*>(gate));
 }
@@ -73,10 +87,15 @@ NAFAE_API int nafae_gate_wait(void* gate, int slot, cudaStream_t stream) {
   return nafae::launch_status("gate_wait_kernel");
 }
 
+NAFAE_API int nafae_gate_sync(void* gate, cudaStream_t stream) {
+  NAFAE_REQUIRE(gate != nullptr, "gate_sync: NULL gate");
+  nafae::gate_sync_kernel<<<1, 32, 0, stream>>>(static_cast<int*>(gate));
+  return nafae::launch_status("gate_sync_kernel");
+}
+
 NAFAE_API int nafae_set_reserved_sms(int n) {
-  const int prev = nafae::g_reserved_sms;
-  nafae::g_reserved_sms = n < 0 ? 0 : n;
-  return prev;
+  return nafae::g_reserved_sms[nafae::current_device_slot()].exchange(n < 0 ? 0 : n,
+                                                                      std::memory_order_relaxed);
 }
 
 NAFAE_API int nafae_abi_version(void) { return NAFAE_B200_ABI_VERSION; }

@@ -35,7 +35,9 @@ class _Ground(torch.autograd.Function):
                                              _C.ptr(D_ind), _C.ptr(D_sim), _C.ptr(loss),
                                              _C.ptr(ws), ws.numel() * 4, _C.stream(dev))
         _C.check(st, "nafae_ground_forward")
-        needs_bwd = vis_feats.requires_grad or word_feats.requires_grad
+        # a backward can only follow when a graph is being recorded (not under torch.no_grad(), the
+        # usual validation loop over live modules): otherwise the workspace goes straight back
+        needs_bwd = torch.is_grad_enabled() and (vis_feats.requires_grad or word_feats.requires_grad)
         ctx.cfg = (dims, float(Delta), float(vis_lam), int(train))
         ctx.pool = pool
         if needs_bwd:
@@ -52,6 +54,10 @@ class _Ground(torch.autograd.Function):
         (Na, Ns, Nb, Ne, D), Delta, vis_lam, train = ctx.cfg
         vis, word, lens, D_ind, D_sim = ctx.saved_tensors
         ws = ctx.ws
+        if ws is None:
+            raise RuntimeError("nafae_b200 DVSA: the fused backward consumes the forward's workspace; a "
+                               "second backward through the same forward (retain_graph=True) is not "
+                               "supported -- run the forward again")
         dev = vis.device
         g_loss = g_loss.to(dtype=torch.float32).contiguous()
         gvis = torch.empty_like(vis)

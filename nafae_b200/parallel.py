@@ -132,10 +132,15 @@ class PeerAllReduce(object):
     every rank must call it the same number of times.  torch.distributed is only used once, to
     exchange the 64-byte IPC handles."""
 
-    def __init__(self, numel, device, rank=None, world=None, num_ctas=None, cta_threads=None):
+    kind = "peer"
+
+    def __init__(self, numel, device, rank=None, world=None, num_ctas=None, cta_threads=None,
+                 variant=0, width=0):
         import ctypes
         from . import _C
         self._C, self._ct = _C, ctypes
+        # include/nafae_b200.h: NAFAE_AR_VARIANT(v) | NAFAE_AR_WIDTH(w)
+        self.flags = (int(variant) & 0xf) | ((int(width) & 0xff) << 8)
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.dev = torch.device(device)
@@ -189,7 +194,7 @@ class PeerAllReduce(object):
             return
         with torch.cuda.device(self.dev):
             st = self._C.lib.nafae_allreduce_avg(self._ptrs, self.rank, self.world, self.count,
-                                                 self.num_ctas, self.cta_threads,
+                                                 self.num_ctas, self.cta_threads, self.flags,
                                                  self._C.stream(self.dev))
         self._C.check(st, "nafae_allreduce_avg")
 
@@ -204,6 +209,171 @@ class PeerAllReduce(object):
             self.buf = None
             self._C.lib.nafae_ar_free(self._ct.c_void_p(self._own))
             self._own = None
+
+
+def _share_fd_from_root(fd, rank, world, root=0):
+    """Hand one file descriptor from `root` to every other rank of the (single-node) group over
+    an abstract AF_UNIX socket with SCM_RIGHTS.  Returns the received descriptor (root: `fd`)."""
+    import socket
+    import time
+    name = [None]
+    srv = None
+    if rank == root:
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        name[0] = "\0nafae-b200-mc-%d-%d" % (os.getpid(), int(time.time() * 1e6) & 0xffffffff)
+        srv.bind(name[0])
+        srv.listen(world)
+    dist.broadcast_object_list(name, src=root)
+    got = fd
+    if rank == root:
+        for _ in range(world - 1):
+            conn, _addr = srv.accept()
+            socket.send_fds(conn, [b"f"], [fd])
+            conn.recv(1)  # the peer has the descriptor: safe to close
+            conn.close()
+        srv.close()
+    else:
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        for attempt in range(200):
+            try:
+                c.connect(name[0])
+                break
+            except (ConnectionRefusedError, FileNotFoundError):
+                time.sleep(0.01)
+        else:
+            raise RuntimeError("could not reach the multicast root's socket")
+        _msg, fds, _flags, _addr = socket.recv_fds(c, 16, 1)
+        c.send(b"k")
+        c.close()
+        if not fds:
+            raise RuntimeError("no file descriptor received from the multicast root")
+        got = fds[0]
+    return got
+
+
+def multicast_supported(device=None):
+    """True when the current device can bind memory to an NVSwitch multicast object (NVLS)."""
+    from . import _C
+    if not torch.cuda.is_available():
+        return False
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        return int(_C.lib.nafae_mc_supported()) == 1
+
+
+class MulticastAllReduce(object):
+    """Flat fp32 gradient bucket in NVSwitch MULTICAST memory + the in-switch (NVLS) all-reduce
+    kernel of csrc/allreduce.cu (`allreduce_mc_kernel`: multimem.ld_reduce / multimem.st).
+
+    Same interface as `PeerAllReduce`.  torch.distributed is only used during construction
+    (to pass the multicast object's file descriptor around and for two host barriers)."""
+    kind = "multicast"
+
+    def __init__(self, numel, device, rank=None, world=None, num_ctas=None, cta_threads=None):
+        import ctypes
+        from . import _C
+        self._C, self._ct = _C, ctypes
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.dev = torch.device(device)
+        pad = 4 * self.world
+        self.count = (int(numel) + pad - 1) // pad * pad
+        self.numel = int(numel)
+        self.cta_threads = int(cta_threads if cta_threads is not None else
+                               os.environ.get("NAFAE_MC_THREADS", "512"))
+        self.num_ctas = int(num_ctas if num_ctas is not None else os.environ.get("NAFAE_MC_CTAS", "16"))
+        nbytes = int(_C.lib.nafae_mc_buffer_bytes(self.count, self.world))
+        h = ctypes.c_void_p()
+        self._h = None
+        with torch.cuda.device(self.dev):
+            # every rank reports whether it can go on BEFORE anyone blocks in a collective step
+            ok = [None] * self.world
+            fd = ctypes.c_int(-1)
+            err = ""
+            if self.rank == 0:
+                st = int(_C.lib.nafae_mc_create(self.world, nbytes, ctypes.byref(h), ctypes.byref(fd)))
+                if st != 1:
+                    err = _C.last_error()
+            dist.all_gather_object(ok, err)
+            if ok[0]:
+                raise RuntimeError("nafae_mc_create failed on rank 0: %s" % ok[0])
+            got = _share_fd_from_root(int(fd.value), self.rank, self.world)
+            err = ""
+            if self.rank != 0:
+                st = int(_C.lib.nafae_mc_import(int(got), self.world, nbytes, ctypes.byref(h)))
+                if st != 1:
+                    err = _C.last_error()
+            try:
+                os.close(int(got))
+            except OSError:
+                pass
+            if not err:
+                if int(_C.lib.nafae_mc_add_device(h)) != 1:
+                    err = _C.last_error()
+            dist.all_gather_object(ok, err)
+            if any(ok):
+                raise RuntimeError("multicast setup failed: %s" % [e for e in ok if e])
+            uc, mc = ctypes.c_void_p(), ctypes.c_void_p()
+            err = ""
+            if int(_C.lib.nafae_mc_bind(h, ctypes.byref(uc), ctypes.byref(mc))) != 1:
+                err = _C.last_error()
+            dist.all_gather_object(ok, err)
+            if any(ok):
+                raise RuntimeError("multicast bind failed: %s" % [e for e in ok if e])
+        self._h, self._uc, self._mc = h, uc.value, mc.value
+        off = int(_C.lib.nafae_ar_data_offset())
+        self.buf = torch.as_tensor(_RawCudaArray(self._uc + off, self.count), device=self.dev)[: self.numel]
+        dist.barrier()
+
+    views = PeerAllReduce.views
+
+    def launch(self):
+        """All-reduce (AVG) the bucket in place on the current stream."""
+        if self.world <= 1:
+            return
+        with torch.cuda.device(self.dev):
+            st = self._C.lib.nafae_allreduce_mc(self._ct.c_void_p(self._uc), self._ct.c_void_p(self._mc),
+                                                self.rank, self.world, self.count, self.num_ctas,
+                                                self.cta_threads, self._C.stream(self.dev))
+        self._C.check(st, "nafae_allreduce_mc")
+
+    def timed_out(self):
+        """Host-synchronising: did a cross-GPU wait of this bucket ever time out?"""
+        with torch.cuda.device(self.dev):
+            return int(self._C.lib.nafae_allreduce_mc_error(self._ct.c_void_p(self._uc))) != 0
+
+    def close(self):
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()
+        if self._h is not None:
+            self.buf = None
+            with torch.cuda.device(self.dev):
+                self._C.lib.nafae_mc_free(self._h)
+            self._h = None
+        dist.barrier()
+
+
+def make_allreduce(numel, device, kind="auto", peer_kw=None, mc_kw=None):
+    """The gradient all-reduce of the data-parallel step: `multicast` (NVLS, in-switch reduction)
+    when every rank's device supports it, else `peer` (bulk-copy two-shot over CUDA-IPC peer
+    memory).  `kind` = "auto" | "multicast" | "peer"; all ranks take the same decision."""
+    if kind not in ("auto", "multicast", "peer"):
+        raise ValueError("kind must be auto, multicast or peer")
+    if kind != "peer":
+        mine = multicast_supported(device)
+        flags = [None] * dist.get_world_size()
+        dist.all_gather_object(flags, bool(mine))
+        if all(flags):
+            try:
+                return MulticastAllReduce(numel, device, **(mc_kw or {}))
+            except RuntimeError as e:  # raised collectively (every rank sees the same failure)
+                if kind == "multicast":
+                    raise
+                import sys
+                print("nafae_b200: NVLS multicast setup failed (%s); using the peer-memory all-reduce" % e,
+                      file=sys.stderr)
+        elif kind == "multicast":
+            raise RuntimeError("NVSwitch multicast is not supported on every rank: %s" % flags)
+    return PeerAllReduce(numel, device, **(peer_kw or {}))
 
 
 def capture_step_with_allreduce(step, reduce_bucket, side_stream):

@@ -18,7 +18,8 @@ class GroundingStep(object):
     KERNELS_PER_STEP_EVAL = 3
 
     def __init__(self, Na, Ns, Nb, Ne, D, C, H, W, n_props, pre_nms_topn=6000, nms_thresh=0.7,
-                 spatial_scale=1.0 / 16.0, Delta=10.0, vis_lam=4.13, train=True, device=None):
+                 spatial_scale=1.0 / 16.0, Delta=10.0, vis_lam=4.13, train=True, device=None,
+                 l1_loss=True):
         self.dev = torch.device(device if device is not None else
                                 "cuda:%d" % torch.cuda.current_device())
         self.dims = (Na, Ns, Nb, Ne, D)
@@ -41,7 +42,10 @@ class GroundingStep(object):
         self.D_ind = torch.empty((self.F, self.NQ), dtype=torch.int64, device=self.dev)
         self.D_sim = torch.empty((self.F, self.NQ), **f32)
         self.loss = torch.zeros((), **f32)
-        self.grad_loss = torch.ones((), **f32)
+        # upstream gradient of margin_loss.  l1_loss: the step wrapper's L1Loss(margin_loss, 0)
+        # (reference model.py:771) -> sign(margin_loss), taken by the backward kernel from the
+        # forward's workspace (NULL pointer); otherwise a device scalar the caller may overwrite
+        self.grad_loss = None if l1_loss else torch.ones((), **f32)
         self.grad_vis = torch.empty((self.R, D), **f32)
         self.grad_word = torch.empty((self.NQ, D), **f32)
         nbytes = int(_C.lib.nafae_ground_workspace_bytes(*self.dims))
@@ -93,6 +97,12 @@ class GroundingStep(object):
                                                _C.ROI_ALIGN_WS_BYTES if gated else 0, _C.stream(self.dev)),
                      "nafae_roi_align_forward")
 
+    def sync_gate(self):
+        """Mark every gated RoIAlign launch so far as seen by all waiting branches (enqueue after
+        gated launches that had no `wait_gate` partner, e.g. warm-up, before paired use)."""
+        with torch.cuda.device(self.dev):
+            _C.check(_C.lib.nafae_gate_sync(_C.ptr(self.gate), _C.stream(self.dev)), "nafae_gate_sync")
+
     def wait_gate(self, slot):
         """Hold the current stream until this step's gated RoIAlign kernel owns its SMs."""
         with torch.cuda.device(self.dev):
@@ -104,7 +114,7 @@ class GroundingStep(object):
         706-707): independent of the trainable weights, so it may run ahead of / concurrently with
         earlier batches' head (see `capture_pipelined`)."""
         self.run_tail()
-        self.run_align()
+        self.run_align(gated=False)  # nobody waits on the gate in the sequential form
 
     def run_head(self, backward=None):
         """Head half: similarity + losses forward, then backward to dL/dvis_feats, dL/dword_feats.
@@ -170,6 +180,8 @@ def capture_pipelined(align_step, next_step, streams, extra_branch=None, gate_he
     on the SMs where its long-lived CTAs sit.  A branch that must NOT spread over the GPU (the
     all-reduce: its CTAs spin on peers) waits behind the kernel's residency gate (`wait_gate`);
     `gate_head=True` does the same for the head (measured slower: its kernels want the whole GPU)."""
+    align_step.sync_gate()  # eager: earlier unpaired gated launches must not satisfy this graph's waits
+    torch.cuda.current_stream().synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         capture_pipelined_body(align_step, next_step, streams, extra_branch, gate_head)

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     assert not _C.MISSING
     assert set(_declared_symbols()) == set(_C.SIGNATURES), "ctypes table out of sync with the header"
-    assert lib.nafae_abi_version() == 2
+    assert lib.nafae_abi_version() == 3 == _C.ABI_VERSION
 
 
 def test_invalid_arguments_return_zero_without_a_gpu():
@@ -130,6 +130,37 @@ def test_allreduce_abi_argument_checks_without_a_gpu():
     assert _C.lib.nafae_ar_buffer_bytes(n, 8) >= n * 4 + _C.lib.nafae_ar_data_offset()
     assert _C.lib.nafae_ar_buffer_bytes(5, 8) == _C.lib.nafae_ar_data_offset() + 32 * 4  # padded to 4*world
     ptrs = (ctypes.c_void_p * 2)()
-    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 9, 64, 8, 128, None) == 0        # world > 8
-    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 2, 10, 8, 128, None) == 0        # count not padded
-    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 1, 64, 8, 256, None) == 1        # world 1: nothing to do
+    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 9, 64, 8, 128, 0, None) == 0        # world > 8
+    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 2, 10, 8, 128, 0, None) == 0        # count not padded
+    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 1, 64, 8, 256, 0, None) == 1        # world 1: nothing to do
+    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 2, 64, 8, 7, 0, None) == 0          # bad cta_threads
+
+
+def test_multicast_and_optimizer_abi_argument_checks_without_a_gpu():
+    from nafae_b200 import _C
+    assert _C.lib.nafae_mc_supported() == 0  # no driver / no NVSwitch here: must answer, not crash
+    assert _C.lib.nafae_mc_buffer_bytes(2201600, 8) == _C.lib.nafae_ar_buffer_bytes(2201600, 8)
+    h, fd = ctypes.c_void_p(), ctypes.c_int(-1)
+    assert _C.lib.nafae_mc_create(8, 1 << 20, ctypes.byref(h), ctypes.byref(fd)) <= 0 and _C.last_error()
+    assert _C.lib.nafae_allreduce_mc(None, None, 0, 2, 64, 8, 512, None) == 0      # NULL buffers
+    assert _C.lib.nafae_mc_free(None) == 1
+    assert _C.lib.nafae_clip_adam_workspace_bytes() >= 64
+    assert _C.lib.nafae_clip_adam_step(None, None, None, None, 16, 1e-3, 0.9, 0.999, 1e-8, 1e-5, 100.0,
+                                       None, 0, None) == 0
+    assert _C.lib.nafae_gate_sync(None, None) == 0
+
+
+def test_pure_host_modules_import_without_loading_the_cuda_library():
+    """synth / evaluate / checkpoint / bridge / the sharding helpers must not dlopen
+    libnafae_b200.so (bench.py --impl reference maps only oracle/)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r);"
+            "import nafae_b200, nafae_b200.synth, nafae_b200.evaluate, nafae_b200.checkpoint,"
+            " nafae_b200.bridge, nafae_b200.parallel;"
+            "assert nafae_b200.parallel.shard_segments(10, 1, 4) == (3, 6);"
+            "assert 'nafae_b200._C' not in sys.modules;"
+            "assert 'libnafae_b200' not in open('/proc/self/maps').read();"
+            "print('ok')") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr

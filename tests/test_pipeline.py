@@ -151,7 +151,7 @@ def test_cfg5_inference_sweep_sample_picks_and_boxes():
 @gpu
 def test_symmetric_buffer_alloc_and_world1_allreduce_is_identity():
     """The IPC-mapped gradient bucket: allocation, torch view, world-1 launch (multi-rank behaviour is
-    exercised by tools/test_allreduce.py under torchrun and by bench.py --gpus N)."""
+    exercised by tests/test_multi_gpu.py and by bench.py --gpus N)."""
     import ctypes
     from nafae_b200 import _C
     from nafae_b200.parallel import _RawCudaArray
@@ -166,7 +166,7 @@ def test_symmetric_buffer_alloc_and_world1_allreduce_is_identity():
     assert float(buf.abs().sum()) == 0.0  # zero-filled
     buf.copy_(torch.arange(n, dtype=torch.float32, device="cuda:0"))
     ptrs = (ctypes.c_void_p * 1)(own.value)
-    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 1, n, 8, 128, _C.stream()) == 1
+    assert _C.lib.nafae_allreduce_avg(ptrs, 0, 1, n, 8, 128, 0, _C.stream()) == 1
     torch.cuda.synchronize()
     assert torch.equal(buf.cpu(), torch.arange(n, dtype=torch.float32))
     del buf
@@ -211,3 +211,68 @@ def test_residency_gate_releases_a_concurrent_branch():
     assert _C.lib.nafae_roi_align_forward(_C.ptr(st.features), st.scale, st.F, st.R, st.H, st.W, st.C, 7, 7,
                                           _C.POOL_AVG, _C.ptr(st.rois), _C.ptr(st.pooled), 0,
                                           _C.ptr(st.gate), 8, _C.stream()) == 0
+
+
+@gpu
+@pytest.mark.timeout(100, method="thread")
+def test_gate_wait_after_unpaired_launches_blocks_until_the_next_open():
+    """a gated launch without a waiter (warm-up) must not satisfy a LATER wait.  After
+    nafae_gate_sync a waiter really blocks until the concurrent launch opens the gate; without it
+    the stale epoch lets it through at once (the round-1 lag, kept visible here)."""
+    import time
+    from nafae_b200.pipeline import GroundingStep
+    dev = torch.device("cuda:0")
+    F, C, H, W = 4, 64, 38, 50
+    c = dict(synth.CONFIGS["cfg2"], Na=1, Ns=F, C=C, H=H, W=W, n=300, img_h=H * 16, img_w=W * 16)
+    st = GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], C, H, W, c["n"], device=dev)
+    st.load(synth.make_batch(c, 3))
+    st.run_tail()
+    side = torch.cuda.Stream(dev)
+    marks = torch.zeros(3, device=dev)
+    st.run_align(gated=True)           # epoch 1, nobody waits
+    with torch.cuda.stream(side):      # (also loads the wait / fill kernels before anything spins)
+        side.wait_stream(torch.cuda.current_stream())
+        st.wait_gate(0)
+        marks[0:1].fill_(1.0)
+    torch.cuda.synchronize()
+    st.run_align(gated=True)           # epoch 2: UNPAIRED -- slot 0 has only seen epoch 1
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):      # stale: passes without any concurrent launch
+        st.wait_gate(0)
+        marks[1:2].fill_(1.0)
+    torch.cuda.synchronize()
+    assert float(marks[1]) == 1.0
+    st.run_align(gated=True)           # unpaired again, then resynchronise
+    st.sync_gate()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        st.wait_gate(0)
+        marks[2:3].fill_(1.0)
+    time.sleep(0.2)
+    assert not side.query(), "the waiter passed although no launch has opened the gate since the sync"
+    want = st.pooled.clone()
+    st.run_align(gated=True)           # the launch this wait belongs to
+    torch.cuda.synchronize()
+    assert float(marks[2]) == 1.0 and torch.equal(st.pooled, want)
+
+
+@gpu
+def test_l1_loss_sign_comes_from_the_forward_workspace():
+    """GroundingStep(l1_loss=True) passes no upstream gradient: the backward uses sign(margin_loss)
+    (model.py:771) -- same gradients as an explicit +1 for a positive loss."""
+    from nafae_b200.pipeline import GroundingStep
+    c = synth.CONFIGS["cfg2"]
+    b = synth.make_batch("cfg2", 9)
+    outs = []
+    for l1 in (True, False):
+        st = GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], 8, c["H"], c["W"], 64,
+                           Delta=c["Delta"], vis_lam=c["vis_lam"], train=True, device="cuda:0", l1_loss=l1)
+        st.vis_feats.copy_(torch.from_numpy(b["vis_feats"]))
+        st.word_feats.copy_(torch.from_numpy(b["word_feats"]))
+        st.lens.copy_(torch.tensor(b["lens"], dtype=torch.int32))
+        st.run_head()
+        torch.cuda.synchronize()
+        assert float(st.loss) > 0
+        outs.append((st.grad_word.clone(), st.grad_vis.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-7)  # clustering atomics: order
