@@ -28,6 +28,7 @@ SIGNATURES = {
     "nafae_set_reserved_sms": (c_int, [c_int]),
     "nafae_gate_wait": (c_int, [c_void_p, c_int, c_void_p]),
     "nafae_gate_sync": (c_int, [c_void_p, c_void_p]),
+    "nafae_debug_occupy_sms": (c_int, [c_int, c_int, ctypes.c_ulonglong, c_void_p]),
     "nms_cuda_compute": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float]),
     "nafae_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nafae_nms_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
@@ -98,6 +99,7 @@ if not MISSING and int(lib.nafae_abi_version()) != ABI_VERSION:
 
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 FLAG_EXACT = 1
+FLAG_NO_GATE = 2
 GATE_BYTES = 32
 ROI_ALIGN_WS_BYTES = 64
 

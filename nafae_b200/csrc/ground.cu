@@ -859,14 +859,64 @@ __global__ void __launch_bounds__(kBwdThreads, 2) ground_bwd_kernel(const BwdPar
       __syncthreads();
     }
     if (bid == 0 && tid == 0) st_release(flag, 1);  // ordered after the CTA's stores by the barrier
-  } else if (bid < d.F + d.NQ) {
+  } else {
+    // Column roles are dealt by LIVE rank, so that the CTAs with real work are dispatched first
+    // (blockIdx order) and the rest -- zero-fill of a masked dL/dword row, or nothing -- trail:
+    //   [F, F+nlive)            dL/dword of live column #k
+    //   [F+nlive, F+2 nlive)    (train) clustering gradient of live column #k
+    //   then                    one masked column each: dL/dword row = 0
+    __shared__ int s_col;   // column this CTA serves
+    __shared__ int s_role;  // 0 word, 1 cluster, 2 zero-fill, 3 nothing
+    if (tid < 32) {
+      const int want = bid - d.F;
+      int nlive = 0, ndead = 0, col_live = -1, col_dead = -1;
+      // first pass: count; the k-th live / dead column is located in the same sweep
+      int nl_tot = 0;
+      for (int c0 = 0; c0 < d.NQ; c0 += 32) {
+        const int c = c0 + lane;
+        const bool lv = c < d.NQ && (c % d.Ne) < __ldg(p.lens + c / d.Ne);
+        nl_tot += __popc(__ballot_sync(0xffffffffu, lv));
+      }
+      const int k_live = want < nl_tot ? want : (p.train && want < 2 * nl_tot ? want - nl_tot : -1);
+      const int k_dead = want - (p.train ? 2 : 1) * nl_tot;
+      for (int c0 = 0; c0 < d.NQ; c0 += 32) {
+        const int c = c0 + lane;
+        const bool in = c < d.NQ;
+        const bool lv = in && (c % d.Ne) < __ldg(p.lens + c / d.Ne);
+        const unsigned bl = __ballot_sync(0xffffffffu, lv), bd = __ballot_sync(0xffffffffu, in && !lv);
+        const int pl = nlive + __popc(bl & ((1u << lane) - 1u)), pd = ndead + __popc(bd & ((1u << lane) - 1u));
+        if (lv && pl == k_live) col_live = c;
+        if (in && !lv && pd == k_dead) col_dead = c;
+        nlive += __popc(bl);
+        ndead += __popc(bd);
+      }
+      // exactly one lane (or none) found its column: reduce with max
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        col_live = max(col_live, __shfl_xor_sync(0xffffffffu, col_live, o));
+        col_dead = max(col_dead, __shfl_xor_sync(0xffffffffu, col_dead, o));
+      }
+      if (lane == 0) {
+        if (k_live >= 0) {
+          s_col = col_live;
+          s_role = want < nl_tot ? 0 : 1;
+        } else {
+          s_col = col_dead;
+          s_role = col_dead >= 0 ? 2 : 3;
+        }
+      }
+    }
+    __syncthreads();
+    const int role = s_role;
+    if (role == 2) {
+      float* dst = p.gword + (size_t)s_col * d.D;
+      for (int k = tid; k < d.D; k += kBwdThreads) dst[k] = 0.f;
+    } else if (role == 0) {
     // ----------------------------------------------------------------- dL/dword ----
-    const int c = bid - d.F, a2 = c / d.Ne;
+    const int c = s_col, a2 = c / d.Ne;
     float* dst = p.gword + (size_t)c * d.D;
     const int len = __ldg(p.lens + a2);
-    if ((c % d.Ne) >= len) {
-      for (int k = tid; k < d.D; k += kBwdThreads) dst[k] = 0.f;
-    } else {
+    {
       float* xcol = sm;                                  // [F]
       float* hcol = xcol + d.F;                          // [F]
       float* g = hcol + d.F;                             // [F]
@@ -893,11 +943,11 @@ __global__ void __launch_bounds__(kBwdThreads, 2) ground_bwd_kernel(const BwdPar
         dst[k] = accv;
       }
     }
-  } else {
+    } else if (role == 1) {
     // ------------------------------------------------ clustering-loss gradient ----
-    const int c = bid - d.F - d.NQ, a = c / d.Ne, e = c % d.Ne;
+    const int c = s_col, a = c / d.Ne;
     const float dem = __ldg(w.scal + 1);
-    if (e < __ldg(p.lens + a) && dem > 0.f) {
+    if (dem > 0.f) {
       float* rows = sm;                       // [Ns][D] the picked rows of this entity
       float* Vsum = rows + (size_t)d.Ns * d.D;
       float* simn = Vsum + d.D;
@@ -979,6 +1029,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) ground_bwd_kernel(const BwdPar
           atomicAdd(p.gvis + (size_t)row[s] * d.D + k, gu * iv - xv * c2);
         }
       }
+    }
     }
   }
   // last CTA out resets the scratch words for the next launch

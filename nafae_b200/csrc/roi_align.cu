@@ -230,35 +230,51 @@ align_bwd_generic(const float* __restrict__ top_diff, const float* __restrict__ 
 //
 // Persistent CTAs (one per SM).  Work unit = (frame, group of cg channels): its NCHW slab is
 // contiguous in HBM and is staged into shared memory by 1-D bulk async copies (TMA engine) through
-// a ring of `stages` buffers with full/empty mbarriers: a dedicated producer warp keeps the ring
-// full, 16 consumer warps drain it and never meet at a CTA-wide barrier except when the frame
-// (and with it the RoI table) changes.  Pass-groups (RoI x 4*CPL channels) are dealt round-robin
-// to the consumer warps across unit boundaries, so a 20-RoI frame keeps 16 warps evenly busy.
-// Inside a pass a lane owns one sample column (pw) of CPL channels: the RoI's row offsets and
-// weights are warp-uniform table reads, the taps are LDS with compile-time offsets (W and the
-// padded channel stride are template constants for the two production map sizes), the 2x2 pool is
-// one shuffle per sample row.  For POOL_AVG the 1/4 is folded into the column weights.
-// The kernel is bound by the shared-memory / L1 data stage, not by arithmetic, so two things keep
-// the number of wavefronts down: (a) a sample row whose cell rows equal (or follow by one) the
-// previous sample row's reuses the horizontally interpolated rows it already holds (RoIs shorter
-// than 7 cells -- half of them -- need ~6 row loads instead of 16); (b) the pooled 7x7 blocks of a
-// pass (4*CPL consecutive channels of one RoI = 784*CPL contiguous bytes of the output) are staged
-// in a per-warp shared buffer and leave with ONE bulk store (cp.async.bulk shared -> global)
-// instead of 7*CPL scattered 28-byte-per-channel stores.
+// a ring of `stages` buffers with full/empty mbarriers.
+//
+// PRODUCER WARP (all 32 lanes) -- scheduling, loads and RoI tables:
+//   * units are CLAIMED dynamically, with frame affinity: one claim counter per frame in the
+//     workspace; CTA b starts at frame b*B/grid (so ~grid/B CTAs share a frame, as a static split
+//     would) and moves on to the nearest frame with unclaimed units when its own runs dry.  A CTA
+//     that starts late (a concurrent kernel still holds its SM) or draws expensive frames simply
+//     claims fewer units: the kernel ends when the work ends, not when the unluckiest static share
+//     ends (round 1: avg 73.0 k vs max 84.5 k active cycles per SM).  Near the end of its expected
+//     share a CTA claims only one unit ahead of the one being processed (instead of stages-1), so
+//     the tail is at most about one unit.  Without a workspace the split is static and contiguous.
+//   * the RoI table of a frame (cells + weights of its 8x8 sample grid per RoI) is built by the
+//     producer warp into one of two half buffers while the slab is in flight; consumer warps never
+//     build tables and never meet at a CTA-wide barrier.  Frames with more than half / all of the
+//     table capacity use the whole buffer / several chunks (the slab is then issued once per chunk).
+//   * lane 0 issues the bulk copies; a stage is published (second arrival on its full barrier) with
+//     a small descriptor (frame, channel group, table range).
+// CONSUMER WARPS (16): pass-groups (RoI x 4*CPL channels) are dealt round-robin to the warps across
+// unit boundaries, so a 20-RoI frame keeps 16 warps evenly busy.  Inside a pass a lane owns one
+// sample column (pw) of CPL channels: the RoI's row offsets and weights are warp-uniform table
+// reads, the taps are LDS with compile-time offsets (W and the padded channel stride are template
+// constants for the two production map sizes), the 2x2 pool is one shuffle per sample row.  For
+// POOL_AVG the 1/4 is folded into the column weights.
+// The kernel is bound by instruction issue and the shared-memory data stage, not by arithmetic, so:
+// (a) a sample row whose cell rows equal (or follow by one) the previous sample row's reuses the
+// horizontally interpolated rows it already holds (RoIs shorter than 7 cells -- half of them --
+// need ~6 row loads instead of 16); (b) the pooled 7x7 blocks of a pass (4*CPL consecutive channels
+// of one RoI = 784*CPL contiguous bytes of the output) are staged in a per-warp shared buffer and
+// leave with ONE bulk store (cp.async.bulk shared -> global).
 constexpr int kOut = 7;
 constexpr int kS = 8;               // sample grid side
 #ifndef NAFAE_CONS_WARPS
 #define NAFAE_CONS_WARPS 16
 #endif
-#ifndef NAFAE_SLAB_PREDICATED
-#define NAFAE_SLAB_PREDICATED 0
-#endif
 constexpr int kConsWarps = NAFAE_CONS_WARPS;
 constexpr int kConsThreads = kConsWarps * 32;
 constexpr int kSlabThreads = kConsThreads + 32;  // + producer warp
-constexpr int kMaxRoiTable = 104;   // RoIs of one frame resident in the table at a time
+constexpr int kTabCap = 104;        // RoI table entries in shared memory
+constexpr int kTabHalf = kTabCap / 2;
 constexpr int kStagesMax = 4;
-constexpr int kPreFrames = 4;      // frames whose RoI tables a CTA may hold at once (prebuilt)
+constexpr int kFrRegs = 32;         // frame ids cached per producer lane (R <= 1024)
+// workspace words (ints): [0] residency arrivals, [1] gate epoch, [2..7] epochs seen per waiting slot,
+// [8] exit ticket, [16 + f] claim counter of frame f
+constexpr int kWsExit = 8;
+constexpr int kWsSched = 16;
 
 struct __align__(16) RoiEntry {  // 192 B: everything a pass needs about one RoI
   int hoff_b[kS];   // byte offset of row hstart (hstart*W*4); 0 if the sample row is outside
@@ -281,45 +297,51 @@ struct SlabParams {
   int hwp;         // padded per-channel stride in shared memory (floats), hwp % 32 == 8
   int stages;
   int units;       // B * groups
-  int* gate;       // optional residency gate (nafae_gate_wait): [0] arrivals, [1] epoch
+  int* gate;       // optional workspace: residency gate (nafae_gate_wait) ...
+  int* sched;      // ... and per-frame claim counters (NULL: static contiguous split)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cons_barrier() {  // the 16 consumer warps only
-  asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory");
+
+// one axis of a RoI's sample grid (roi_geom restricted to one axis: one double division)
+__device__ __forceinline__ void roi_axis(const float* __restrict__ roi, float scale, bool is_w,
+                                         float* start, float* bin) {
+  const float lo = __ldg(roi + (is_w ? 1 : 2)), hi = __ldg(roi + (is_w ? 3 : 4));
+  const float st = __fmul_rn(lo, scale);
+  const float ext = fmaxf(__fadd_rn(__fmaf_rn(hi, scale, -st), 1.f), 0.f);
+  *start = st;
+  *bin = __double2float_rn(__ddiv_rn((double)ext, __dsub_rn((double)kS, 1.)));
 }
 
 template <int POOL, int W_CT, int HWP_CT, int CPL, int NBLK_CT>
 __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const SlabParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [stages][cg][hwp] floats | RoiEntry[kMaxRoiTable] | int roi_id[kMaxRoiTable] | bars |
-  //         per-warp output staging
+  // layout: [stages][cg][hwp] floats | RoiEntry[kTabCap] | int roi_id[kTabCap] | int scan[kTabCap] |
+  //         full/empty barriers | per-warp output staging
   float* slabs = reinterpret_cast<float*>(smem_raw);
   const int W = W_CT ? W_CT : p.W;
   const int hwp = HWP_CT ? HWP_CT : p.hwp;
   const size_t stage_floats = (size_t)p.cg * hwp;
   RoiEntry* table = reinterpret_cast<RoiEntry*>(slabs + stage_floats * p.stages);
-  int* roi_id = reinterpret_cast<int*>(table + kMaxRoiTable);
-  uint64_t* full = reinterpret_cast<uint64_t*>(roi_id + kMaxRoiTable);
+  int* roi_id = reinterpret_cast<int*>(table + kTabCap);
+  int* scan_list = roi_id + kTabCap;
+  uint64_t* full = reinterpret_cast<uint64_t*>(scan_list + kTabCap);
   uint64_t* empty = full + kStagesMax;
   float* out_stage = reinterpret_cast<float*>(empty + kStagesMax);  // [kConsWarps][4*CPL][7][7]
-  __shared__ int s_nroi, s_next, s_warp_cnt[kConsWarps], s_fbeg[kPreFrames + 1];
+  __shared__ int4 s_desc[kStagesMax];  // per stage: x = frame (< 0: no more work), y = channel group,
+                                       //            z = first table entry, w = number of RoIs
 
   const int tid = threadIdx.x, lane = tid & 31;
   // warp index through a lane-0 broadcast: the compiler then knows it is warp-uniform, and loops whose
-  // bounds depend on it need no collective-reconvergence scaffolding (WARPSYNC.COLLECTIVE / VOTE /
-  // ENDCOLLECTIVE, ~3 instructions per shuffle) around the pooling shuffles
+  // bounds depend on it need no collective-reconvergence scaffolding around the pooling shuffles
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   NAFAE_CTA_TRACE(cta_trace, 1);  // debug builds only
-  // contiguous unit range per CTA: it touches 1-2 frames, whose RoI tables are built once
-  const int u_begin = (int)((long long)p.units * blockIdx.x / gridDim.x);
-  const int u_end = (int)((long long)p.units * (blockIdx.x + 1) / gridDim.x);
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], 2);  // the copies' expect_tx arrival + the "table ready" arrival
       mbar_init(&empty[s], kConsWarps);
     }
     fence_mbar_init();
@@ -333,306 +355,353 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
   __syncthreads();
 
   if (warp == kConsWarps) {
-    // ------------------------------------------------------------ producer warp ----
-    if (lane == 0) {
-      const uint32_t chan_bytes = (uint32_t)p.hw * 4u;
-      for (int u = u_begin; u < u_end; ++u) {
-        const int it = u - u_begin, stage = it % p.stages;
-        if (it >= p.stages) mbar_wait(&empty[stage], (uint32_t)(it / p.stages - 1) & 1u);
-        const int f = u / p.groups, gidx = u % p.groups;
+    // ============================================================ producer warp ====
+    const bool fr_cached = p.R <= kFrRegs * 32;
+    int fr[kFrRegs];  // frame id of RoI lane + 32*i (one L2 round trip, then register scans)
+#pragma unroll
+    for (int i = 0; i < kFrRegs; ++i) {
+      const int r = lane + 32 * i;
+      fr[i] = (fr_cached && r < p.R) ? (int)__ldg(p.rois + (size_t)r * 5) : -1;
+    }
+    const uint32_t chan_bytes = (uint32_t)p.hw * 4u;
+    const bool dynamic = p.sched != nullptr;
+    int cur_f = (int)((long long)p.B * blockIdx.x / gridDim.x);       // dynamic: frame being drained
+    int u_next = (int)((long long)p.units * blockIdx.x / gridDim.x);  // static: contiguous range
+    const int u_end = (int)((long long)p.units * (blockIdx.x + 1) / gridDim.x);
+    const int share = p.units / (int)gridDim.x;  // expected units per CTA
+    int claimed = 0;
+    int it = 0;                     // items published so far
+    int half_f[2] = {-1, -1};       // frame whose complete table sits in half h (-2: part of a whole-buffer table)
+    int half_n[2] = {0, 0};
+    int half_use[2] = {-1, -1};     // last item that reads half h
+    int empty_f = -1;               // a frame known to have no RoIs
+
+    // all consumer warps are done with `item`.  Items older than it - stages have been waited for
+    // already (their stage has been re-armed since: the parity test would alias), so only the
+    // latest user of a stage is ever waited on.
+    auto wait_released = [&](int item) {
+      if (item >= 0 && item >= it - p.stages)
+        mbar_wait(&empty[item % p.stages], (uint32_t)(item / p.stages) & 1u);
+    };
+    // RoIs r >= r0 of frame f, ascending, at most kTabCap of them -> scan_list; returns the count,
+    // *next = where the following chunk starts (>= R: none left)
+    auto scan = [&](int f, int r0, int* next) -> int {
+      int n = 0;
+      *next = p.R;
+      auto step = [&](int base, int frv) -> bool {  // true: list full
+        const int r = base + lane;
+        const bool hit = r < p.R && r >= r0 && frv == f;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        const int cnt = __popc(bal);
+        const int pos = n + __popc(bal & ((1u << lane) - 1u));
+        if (hit && pos < kTabCap) scan_list[pos] = r;
+        if (n + cnt > kTabCap) {
+          *next = base + (int)__fns(bal, 0, kTabCap - n + 1);  // first hit that did not fit
+          n = kTabCap;
+          return true;
+        }
+        n += cnt;
+        if (n == kTabCap) {
+          *next = base + 32;
+          return true;
+        }
+        return false;
+      };
+      if (fr_cached) {
+#pragma unroll
+        for (int i = 0; i < kFrRegs; ++i) {
+          if (32 * i >= p.R) break;
+          if (32 * i + 32 <= r0) continue;
+          if (step(32 * i, fr[i])) break;
+        }
+      } else {
+        bool done = false;
+        for (int base0 = r0 / 32 * 32; base0 < p.R && !done; base0 += 256) {
+          int v[8];  // eight independent loads in flight
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = base0 + 32 * j + lane;
+            v[j] = r < p.R ? (int)__ldg(p.rois + (size_t)r * 5) : -1;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (!done && base0 + 32 * j < p.R) done = step(base0 + 32 * j, v[j]);
+        }
+      }
+      __syncwarp();
+      return n;
+    };
+    // table entries [j0, j0 + n) from scan_list[0, n): one lane per (RoI, axis)
+    auto geometry = [&](int j0, int n) {
+      const float wscale = POOL == NAFAE_POOL_AVG ? 0.25f : 1.f;
+      for (int e = lane; e < 2 * n; e += 32) {
+        const int j = e >> 1;
+        const bool is_w = e & 1;
+        const int r = scan_list[j];
+        float start, bin;
+        roi_axis(p.rois + (size_t)r * 5, p.scale, is_w, &start, &bin);
+        RoiEntry& t = table[j0 + j];
+        if (!is_w) roi_id[j0 + j] = r;
+#pragma unroll
+        for (int k = 0; k < kS; ++k) {
+          int cell;
+          float ratio;
+          const bool ok = axis_sample(start, bin, k, is_w ? p.W : p.H, &cell, &ratio);
+          if (is_w) {
+            t.woff_b[k] = ok ? cell * 4 : 0;
+            t.w0[k] = ok ? wscale * (1.f - ratio) : 0.f;
+            t.w1[k] = ok ? wscale * ratio : 0.f;
+          } else {
+            t.hoff_b[k] = ok ? cell * W * 4 : 0;
+            t.h0[k] = ok ? 1.f - ratio : 0.f;
+            t.h1[k] = ok ? ratio : 0.f;
+          }
+        }
+      }
+      __syncwarp();
+    };
+    // next unit of this CTA, -1 when there is none (warp-uniform)
+    auto claim = [&]() -> int {
+      if (!dynamic) return u_next < u_end ? u_next++ : -1;
+      while (cur_f >= 0) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(p.sched + cur_f, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g < p.groups) return cur_f * p.groups + g;
+        // this frame is fully claimed: nearest frame (cyclically) that still has unclaimed units
+        int found = -1;
+        for (int base = 1; base < p.B && found < 0; base += 32) {
+          const int k = base + lane;
+          int f = cur_f + k;
+          if (f >= p.B) f -= p.B;
+          const bool open = k < p.B && __ldcg(p.sched + f) < p.groups;
+          const unsigned bal = __ballot_sync(0xffffffffu, open);
+          if (bal) {
+            found = cur_f + base + __ffs(bal) - 1;
+            if (found >= p.B) found -= p.B;
+          }
+        }
+        cur_f = found;
+      }
+      return -1;
+    };
+    // publish one item: slab of unit (f, gidx) + table range [j0, j0+n)
+    auto issue_slab = [&](int f, int gidx) {
+      const int stage = it % p.stages;
+      if (lane == 0) {
         const float* src = p.bottom + ((size_t)f * p.C + (size_t)gidx * p.cg) * p.hw;
         float* dst = slabs + stage_floats * stage;
         mbar_arrive_expect_tx(&full[stage], chan_bytes * p.cg);
         for (int c = 0; c < p.cg; ++c)
           bulk_g2s(dst + (size_t)c * hwp, src + (size_t)c * p.hw, chan_bytes, &full[stage]);
       }
+    };
+    auto publish = [&](int f, int gidx, int j0, int n) {
+      const int stage = it % p.stages;
+      __syncwarp();  // table / roi_id stores of all lanes are ordered before lane 0's release-arrive
+      if (lane == 0) {
+        s_desc[stage] = make_int4(f, gidx, j0, n);
+        mbar_arrive(&full[stage]);
+      }
+      ++it;
+    };
+
+    for (;;) {
+      // room for one more item?  normally `stages` deep; near the end of the expected share only
+      // one unit ahead of the one being processed, so that no CTA sits on claimed work at the tail
+      const int depth = (!dynamic || claimed < share - 2) ? p.stages : (p.stages < 2 ? p.stages : 2);
+      wait_released(it - depth);
+      const int u = claim();
+      if (u < 0) break;
+      ++claimed;
+      const int f = u / p.groups, gidx = u - f * p.groups;
+      if (f == empty_f) continue;
+      int h = half_f[0] == f ? 0 : (half_f[1] == f ? 1 : -1);
+      if (h >= 0) {  // table already on chip
+        wait_released(it - p.stages);
+        issue_slab(f, gidx);
+        half_use[h] = it;
+        if (half_f[1] == -2) half_use[1] = it;  // whole-buffer table
+        publish(f, gidx, h * kTabHalf, half_n[h]);
+        continue;
+      }
+      int r_next = 0;
+      int n = scan(f, 0, &r_next);
+      if (n == 0) {
+        empty_f = f;
+        continue;
+      }
+      for (;;) {  // one item per table chunk (a single one unless the frame has > kTabCap RoIs)
+        wait_released(it - p.stages);
+        issue_slab(f, gidx);  // in flight while the table is built
+        const bool whole = n > kTabHalf;
+        if (whole) {
+          wait_released(half_use[0]);
+          wait_released(half_use[1]);
+          h = 0;
+        } else {
+          // the half that is not serving the most recent item
+          h = half_use[0] <= half_use[1] ? 0 : 1;
+          if (half_f[1] == -2) {  // a whole-buffer table is being replaced: both halves must drain
+            wait_released(half_use[0]);
+            wait_released(half_use[1]);
+            half_f[1] = -1;
+            half_f[0] = -1;
+            h = 0;
+          } else {
+            wait_released(half_use[h]);
+          }
+        }
+        geometry(h * kTabHalf, n);
+        const bool complete = r_next >= p.R;
+        half_f[h] = complete ? f : -1;  // only a complete table can be reused by later units
+        half_n[h] = n;
+        half_use[h] = it;
+        if (whole) {
+          half_f[1] = -2;
+          half_use[1] = it;
+        }
+        publish(f, gidx, h * kTabHalf, n);
+        if (complete) break;
+        n = scan(f, r_next, &r_next);
+        if (n == 0) break;
+      }
+    }
+    // no more work: tell the consumers
+    wait_released(it - p.stages);
+    {
+      const int stage = it % p.stages;
+      if (lane == 0) {
+        s_desc[stage] = make_int4(-1, 0, 0, 0);
+        mbar_arrive(&full[stage]);
+        mbar_arrive(&full[stage]);
+      }
+    }
+    // last CTA out leaves the claim counters zeroed for the next launch
+    if (dynamic && lane == 0) {
+      __threadfence();
+      int* exit_ticket = p.sched - kWsSched + kWsExit;
+      if (atomicAdd(exit_ticket, 1) == (int)gridDim.x - 1) {
+        for (int f = 0; f < p.B; ++f) p.sched[f] = 0;
+        *exit_ticket = 0;
+      }
     }
     return;
   }
 
-  // -------------------------------------------------------------- consumer warps ----
-  // Frame ids of RoIs tid, tid + 512, ... stay in registers for the whole kernel: ONE L2 round
-  // trip (in flight while the first slab streams in); every later table scan is register /
-  // shared-memory work only.  (R > kFrCache * 512: scans fall back to global loads.)
-  constexpr int kFrCache = 4;
-  constexpr int kNoFrame = -2147483647 - 1;
-  const bool fr_cached = p.R <= kFrCache * kConsThreads;
-  int fr[kFrCache];
-#pragma unroll
-  for (int i = 0; i < kFrCache; ++i) {
-    const int r = tid + i * kConsThreads;
-    fr[i] = (fr_cached && r < p.R) ? (int)__ldg(p.rois + (size_t)r * 5) : kNoFrame;
-  }
-
+  // ============================================================== consumer warps ====
   // RoIs whose batch index is outside [0, B): defined as all-zero rows (CTA 0 writes them)
   if (blockIdx.x == 0) {
-    auto zero_bad = [&](int base, int b) {  // b = batch index of RoI base + tid
-      unsigned bad = __ballot_sync(0xffffffffu, base + tid < p.R && (b < 0 || b >= p.B));
+    for (int base = 0; base < p.R; base += kConsThreads) {
+      const int r = base + tid;
+      const int b = r < p.R ? (int)__ldg(p.rois + (size_t)r * 5) : 0;
+      unsigned bad = __ballot_sync(0xffffffffu, r < p.R && (b < 0 || b >= p.B));
       while (bad) {
         const int rr = base + warp * 32 + __ffs(bad) - 1;
         bad &= bad - 1;
         float* o = p.top + (size_t)rr * p.C * (kOut * kOut);
         for (int i = lane; i < p.C * kOut * kOut; i += 32) o[i] = 0.f;
       }
-    };
-    if (fr_cached) {
-#pragma unroll
-      for (int i = 0; i < kFrCache; ++i)
-        if (i * kConsThreads < p.R) zero_bad(i * kConsThreads, fr[i]);
-    } else {
-      for (int base = 0; base < p.R; base += kConsThreads)
-        zero_bad(base, base + tid < p.R ? (int)__ldg(p.rois + (size_t)(base + tid) * 5) : 0);
     }
   }
 
-  // One 512-RoI step of a table scan: appends the RoIs base + tid (index >= r_start) of frame f
-  // in ascending index order; true when the table is full.  All consumer warps together.
-  auto scan_step = [&](int f, int r_start, int base, int frv) -> bool {
-    const int r = base + tid;
-    const bool hit = r < p.R && r >= r_start && frv == f;
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-    cons_barrier();
-    const int have = s_nroi;
-    int before = have, tot = 0;
-    for (int w = 0; w < kConsWarps; ++w) {
-      const int cw = s_warp_cnt[w];
-      if (w < warp) before += cw;
-      tot += cw;
-    }
-    const int pos = before + __popc(bal & ((1u << lane) - 1u));
-    if (hit && pos < kMaxRoiTable) roi_id[pos] = r;
-    if (hit && pos == kMaxRoiTable) s_next = r;  // first RoI that did not fit (unique thread)
-    cons_barrier();
-    if (have + tot >= kMaxRoiTable) {  // uniform
-      if (tid == 0) {
-        s_nroi = kMaxRoiTable;
-        if (have + tot == kMaxRoiTable) s_next = min(base + kConsThreads, p.R);
-      }
-      return true;
-    }
-    if (tid == 0) s_nroi = have + tot;
-    return false;
-  };
-  // Appends (from table position pos0) the RoIs of frame f whose index is >= r_start, at most up
-  // to kMaxRoiTable entries; afterwards s_nroi = entries in the table, s_next = index where the
-  // following chunk starts (>= R when the frame is exhausted).
-  auto scan_frame = [&](int f, int r_start, int pos0) {
-    cons_barrier();  // every warp is done with the previous table contents / counters
-    if (tid == 0) {
-      s_nroi = pos0;
-      s_next = p.R;
-    }
-    cons_barrier();
-    if (fr_cached) {
-#pragma unroll
-      for (int i = 0; i < kFrCache; ++i) {
-        const int base = i * kConsThreads;
-        if (base >= p.R) break;
-        if (base + kConsThreads <= r_start) continue;
-        if (scan_step(f, r_start, base, fr[i])) break;
-      }
-    } else {
-      for (int base = r_start / kConsThreads * kConsThreads; base < p.R; base += kConsThreads) {
-        const int r = base + tid;
-        if (scan_step(f, r_start, base, r < p.R ? (int)p.rois[(size_t)r * 5] : kNoFrame)) break;
-      }
-    }
-    cons_barrier();
-  };
-  // geometry of table entries [j_lo, j_hi): one thread per (RoI, axis, sample index)
-  auto geometry = [&](int j_lo, int j_hi) {
-    const float wscale = POOL == NAFAE_POOL_AVG ? 0.25f : 1.f;
-    for (int e = j_lo * 2 * kS + tid; e < j_hi * 2 * kS; e += kConsThreads) {
-      const int j = e / (2 * kS), k = e % (2 * kS);
-      const RoiGeom g = roi_geom(p.rois + (size_t)roi_id[j] * 5, p.scale, kS, kS);
-      int cell;
-      float ratio;
-      if (k < kS) {
-        const bool ok = axis_sample(g.start_h, g.bin_h, k, p.H, &cell, &ratio);
-        table[j].hoff_b[k] = ok ? cell * W * 4 : 0;
-        table[j].h0[k] = ok ? 1.f - ratio : 0.f;
-        table[j].h1[k] = ok ? ratio : 0.f;
-      } else {
-        const bool ok = axis_sample(g.start_w, g.bin_w, k - kS, p.W, &cell, &ratio);
-        table[j].woff_b[k - kS] = ok ? cell * 4 : 0;
-        table[j].w0[k - kS] = ok ? wscale * (1.f - ratio) : 0.f;
-        table[j].w1[k - kS] = ok ? wscale * ratio : 0.f;
-      }
-    }
-    cons_barrier();
-  };
-  auto build_table = [&](int f, int r_start) {  // one (frame, chunk) at a time
-    scan_frame(f, r_start, 0);
-    geometry(0, s_nroi);
-  };
-
-  // Normal case: the RoIs of ALL frames this CTA touches (contiguous unit range: 1-2 frames) fit in
-  // the table together -> built once, here, while the first slab is still in flight; no table work
-  // and no CTA-wide barrier inside the unit loop.  Otherwise: per-(frame, chunk) tables as needed.
-  const int f_first = u_begin / p.groups, f_last = (u_end - 1) / p.groups;
-  bool pre = fr_cached && f_last - f_first < kPreFrames;
-  if (pre) {
-    int pos = 0;
-    for (int f = f_first; f <= f_last; ++f) {
-      if (tid == 0) s_fbeg[f - f_first] = pos;
-      scan_frame(f, 0, pos);
-      if (s_next < p.R) {  // uniform: does not fit
-        pre = false;
-        break;
-      }
-      pos = s_nroi;
-    }
-    if (pre) {
-      if (tid == 0) s_fbeg[f_last - f_first + 1] = pos;
-      geometry(0, pos);
-    }
-  }
-
-  int cur_f = -1, cur_start = -1;  // which (frame, chunk start) the table holds
   // channel blocks per RoI inside a unit (compile-time for the two production shapes: the
   // idx / nblk split below is a 20-instruction integer division otherwise)
   const int nblk = NBLK_CT ? NBLK_CT : p.cg / (4 * CPL);
   const int cq = lane >> 3, pw = lane & 7;
   int g_base = 0;  // running pass-group counter (uniform): deals groups round-robin to warps
   float* my_stage = out_stage + warp * (4 * CPL * kOut * kOut);
-  for (int u = u_begin; u < u_end; ++u) {
-    const int it = u - u_begin;
+  for (int it = 0;; ++it) {
     const int stage = it % p.stages;
-    const uint32_t parity = (uint32_t)(it / p.stages) & 1u;
-    const int f = u / p.groups, gidx = u % p.groups;
+    mbar_wait(&full[stage], (uint32_t)(it / p.stages) & 1u);
+    const int4 d = s_desc[stage];
+    if (d.x < 0) break;
+    const int gidx = d.y, j0 = d.z, nroi = d.w;
+#ifdef NAFAE_TRACE
+    if (tid == 0) CtaTrace::count(cta_trace.idx, 1, nroi);  // items / RoI passes of this CTA
+#endif
     const unsigned char* slab = reinterpret_cast<const unsigned char*>(slabs + stage_floats * stage);
-    bool waited = false;
-    int r_next = 0;
-    do {
-      int j0 = 0, nroi, next_after;
-      if (pre) {
-        j0 = s_fbeg[f - f_first];
-        nroi = s_fbeg[f - f_first + 1] - j0;
-        next_after = p.R;
-      } else {
-        if (!(cur_f == f && cur_start == r_next)) {
-          build_table(f, r_next);
-          cur_f = f;
-          cur_start = r_next;
-        }
-        nroi = s_nroi;
-        next_after = s_next;
+    const int ng = nroi * nblk;
+    for (int idx = warp >= g_base ? warp - g_base : warp - g_base + kConsWarps; idx < ng; idx += kConsWarps) {
+      const int jr = idx / nblk, blk = idx - jr * nblk, j = j0 + jr;
+      const RoiEntry& e = table[j];
+      const float w0 = e.w0[pw], w1 = e.w1[pw];
+      const int ch0 = blk * (4 * CPL) + cq;  // first channel of this lane inside the slab
+      const unsigned char* lane_base = slab + (size_t)ch0 * hwp * 4 + e.woff_b[pw];
+      int hoff[kS];
+      float h0[kS], h1[kS];
+#pragma unroll
+      for (int v = 0; v < kS; v += 4) {
+        const int4 o4 = *reinterpret_cast<const int4*>(&e.hoff_b[v]);
+        const float4 a4 = *reinterpret_cast<const float4*>(&e.h0[v]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&e.h1[v]);
+        hoff[v] = o4.x; hoff[v + 1] = o4.y; hoff[v + 2] = o4.z; hoff[v + 3] = o4.w;
+        h0[v] = a4.x; h0[v + 1] = a4.y; h0[v + 2] = a4.z; h0[v + 3] = a4.w;
+        h1[v] = b4.x; h1[v + 1] = b4.y; h1[v + 2] = b4.z; h1[v + 3] = b4.w;
       }
-      if (!waited) {
-        mbar_wait(&full[stage], parity);
-        waited = true;
-      }
-      const int ng = nroi * nblk;
-      for (int idx = warp >= g_base ? warp - g_base : warp - g_base + kConsWarps; idx < ng; idx += kConsWarps) {
-        const int jr = idx / nblk, blk = idx - jr * nblk, j = j0 + jr;
-        const RoiEntry& e = table[j];
-        const float w0 = e.w0[pw], w1 = e.w1[pw];
-        const int ch0 = blk * (4 * CPL) + cq;  // first channel of this lane inside the slab
-        const unsigned char* lane_base = slab + (size_t)ch0 * hwp * 4 + e.woff_b[pw];
-        int hoff[kS];
-        float h0[kS], h1[kS];
+      // T0/T1: horizontally interpolated cell rows (hstart, hstart+1) of the current sample row;
+      // kept across sample rows while the cell rows repeat or advance by one (warp-uniform tests)
+      float s[CPL][kS], T0[CPL], T1[CPL];
 #pragma unroll
-        for (int v = 0; v < kS; v += 4) {
-          const int4 o4 = *reinterpret_cast<const int4*>(&e.hoff_b[v]);
-          const float4 a4 = *reinterpret_cast<const float4*>(&e.h0[v]);
-          const float4 b4 = *reinterpret_cast<const float4*>(&e.h1[v]);
-          hoff[v] = o4.x; hoff[v + 1] = o4.y; hoff[v + 2] = o4.z; hoff[v + 3] = o4.w;
-          h0[v] = a4.x; h0[v + 1] = a4.y; h0[v + 2] = a4.z; h0[v + 3] = a4.w;
-          h1[v] = b4.x; h1[v + 1] = b4.y; h1[v + 2] = b4.z; h1[v + 3] = b4.w;
-        }
-        // T0/T1: horizontally interpolated cell rows (hstart, hstart+1) of the current sample row;
-        // kept across sample rows while the cell rows repeat or advance by one (warp-uniform tests)
-        float s[CPL][kS], T0[CPL], T1[CPL];
-#if NAFAE_SLAB_PREDICATED
-        // experiment (make pred): the same reuse rule as predicated loads + selects instead of
-        // branches -- no reconvergence / collective-shuffle scaffolding in the pass loop, every
-        // instruction slot is spent but a skipped load costs no shared-memory wavefront
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) T0[k] = T1[k] = 0.f;
-#pragma unroll
-        for (int ph = 0; ph < kS; ++ph) {
-          const int d = ph ? hoff[ph] - hoff[ph - 1] : -1;
-          const bool ld_bot = d != 0;                  // the cell rows changed at all
-          const bool ld_top = ld_bot && d != W * 4;    // ... and not just by one row (top = old bottom)
+      for (int ph = 0; ph < kS; ++ph) {
+        const int dh = ph ? hoff[ph] - hoff[ph - 1] : -1;
+        if (dh != 0) {
           const unsigned char* t = lane_base + hoff[ph];
+          if (dh == W * 4) {
 #pragma unroll
-          for (int k = 0; k < CPL; ++k) {
-            const float* q = reinterpret_cast<const float*>(t + (size_t)k * 4 * hwp * 4);
-            float top = ld_bot ? T1[k] : T0[k];
-            if (ld_top) top = fmaf(q[1], w1, q[0] * w0);
-            float bot = T1[k];
-            if (ld_bot) bot = fmaf(q[W + 1], w1, q[W] * w0);
-            T0[k] = top;
-            T1[k] = bot;
-            s[k][ph] = fmaf(bot, h1[ph], top * h0[ph]);
-          }
-        }
-#else
-#pragma unroll
-        for (int ph = 0; ph < kS; ++ph) {
-          const int d = ph ? hoff[ph] - hoff[ph - 1] : -1;
-          if (d != 0) {
-            const unsigned char* t = lane_base + hoff[ph];
-            if (d == W * 4) {
-#pragma unroll
-              for (int k = 0; k < CPL; ++k) T0[k] = T1[k];
-            } else {
-#pragma unroll
-              for (int k = 0; k < CPL; ++k) {
-                const float* q = reinterpret_cast<const float*>(t + (size_t)k * 4 * hwp * 4);
-                T0[k] = fmaf(q[1], w1, q[0] * w0);
-              }
-            }
+            for (int k = 0; k < CPL; ++k) T0[k] = T1[k];
+          } else {
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
               const float* q = reinterpret_cast<const float*>(t + (size_t)k * 4 * hwp * 4);
-              T1[k] = fmaf(q[W + 1], w1, q[W] * w0);
+              T0[k] = fmaf(q[1], w1, q[0] * w0);
             }
           }
 #pragma unroll
-          for (int k = 0; k < CPL; ++k) s[k][ph] = fmaf(T1[k], h1[ph], T0[k] * h0[ph]);
-        }
-#endif
-        // pooled block -> per-warp staging (channel-major like the output) -> one bulk store
-        if (lane == 0) bulk_wait_read<0>();  // the previous pass's store has drained the buffer
-        __syncwarp();
-        float* o = my_stage + cq * (kOut * kOut) + pw;
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          float* ok = o + k * 4 * (kOut * kOut);
-          if (POOL == NAFAE_POOL_AVG) {
-            float hs_prev = s[k][0] + __shfl_down_sync(0xffffffffu, s[k][0], 1);
-#pragma unroll
-            for (int i = 0; i < kOut; ++i) {
-              const float hs = s[k][i + 1] + __shfl_down_sync(0xffffffffu, s[k][i + 1], 1);
-              if (pw < kOut) ok[i * kOut] = hs_prev + hs;
-              hs_prev = hs;
-            }
-          } else {
-            float right_prev = __shfl_down_sync(0xffffffffu, s[k][0], 1);
-#pragma unroll
-            for (int i = 0; i < kOut; ++i) {
-              const float right_next = __shfl_down_sync(0xffffffffu, s[k][i + 1], 1);
-              const float v = pool4(POOL, s[k][i], right_prev, s[k][i + 1], right_next);
-              if (pw < kOut) ok[i * kOut] = v;
-              right_prev = right_next;
-            }
+          for (int k = 0; k < CPL; ++k) {
+            const float* q = reinterpret_cast<const float*>(t + (size_t)k * 4 * hwp * 4);
+            T1[k] = fmaf(q[W + 1], w1, q[W] * w0);
           }
         }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
-        __syncwarp();
-        if (lane == 0) {
-          const int c_first = gidx * p.cg + blk * (4 * CPL);
-          bulk_s2g(p.top + ((size_t)roi_id[j] * p.C + c_first) * (kOut * kOut), my_stage,
-                   (uint32_t)(4 * CPL * kOut * kOut * sizeof(float)));
-          bulk_commit();
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) s[k][ph] = fmaf(T1[k], h1[ph], T0[k] * h0[ph]);
+      }
+      // pooled block -> per-warp staging (channel-major like the output) -> one bulk store
+      if (lane == 0) bulk_wait_read<0>();  // the previous pass's store has drained the buffer
+      __syncwarp();
+      float* o = my_stage + cq * (kOut * kOut) + pw;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        float* ok = o + k * 4 * (kOut * kOut);
+        if (POOL == NAFAE_POOL_AVG) {
+          float hs_prev = s[k][0] + __shfl_down_sync(0xffffffffu, s[k][0], 1);
+#pragma unroll
+          for (int i = 0; i < kOut; ++i) {
+            const float hs = s[k][i + 1] + __shfl_down_sync(0xffffffffu, s[k][i + 1], 1);
+            if (pw < kOut) ok[i * kOut] = hs_prev + hs;
+            hs_prev = hs;
+          }
+        } else {
+          float right_prev = __shfl_down_sync(0xffffffffu, s[k][0], 1);
+#pragma unroll
+          for (int i = 0; i < kOut; ++i) {
+            const float right_next = __shfl_down_sync(0xffffffffu, s[k][i + 1], 1);
+            const float v = pool4(POOL, s[k][i], right_prev, s[k][i + 1], right_next);
+            if (pw < kOut) ok[i * kOut] = v;
+            right_prev = right_next;
+          }
         }
       }
-      g_base = (g_base + ng) % kConsWarps;  // warp that takes the next pass-group
-      r_next = next_after;
-    } while (r_next < p.R);
-
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk-copy engine
+      __syncwarp();
+      if (lane == 0) {
+        const int c_first = gidx * p.cg + blk * (4 * CPL);
+        bulk_s2g(p.top + ((size_t)roi_id[j] * p.C + c_first) * (kOut * kOut), my_stage,
+                 (uint32_t)(4 * CPL * kOut * kOut * sizeof(float)));
+        bulk_commit();
+      }
+    }
+    g_base = (g_base + ng) % kConsWarps;  // warp that takes the next pass-group
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);  // this warp is done with the stage
   }
@@ -651,14 +720,14 @@ int smem_optin_limit() {
   return cached;
 }
 
-// Persistent grid for `units` equal work units: the units are split statically, so the kernel ends
-// when the CTAs with ceil(units / grid) units end -- use the SMALLEST grid with that same maximum
-// (2560 units on 132 SMs: 20 per CTA either way, but 128 CTAs instead of 132) and leave the other
-// SMs to whatever runs concurrently.
-int slab_grid(int units) {
+// Persistent grid for `units` work units: with dynamic claiming every available SM takes part;
+// with the static split the kernel ends when the CTAs with ceil(units / grid) units end, so use the
+// SMALLEST grid with that same maximum and leave the other SMs to whatever runs concurrently.
+int slab_grid(int units, bool dynamic) {
   int grid = persistent_grid();
   if (grid > units) grid = units;
   if (grid < 1) return 1;
+  if (dynamic) return grid;
   const int per_cta = (units + grid - 1) / grid;
   return (units + per_cta - 1) / per_cta;
 }
@@ -672,7 +741,7 @@ int launch_slab(const SlabParams& p, int pool, size_t smem, cudaStream_t stream)
     set_error("roi_align: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     return -(int)e;
   }
-  const int grid = slab_grid(p.units);
+  const int grid = slab_grid(p.units, p.sched != nullptr);
   kern<<<grid, kSlabThreads, smem, stream>>>(p);
   return launch_status("align_pool_fwd_slab");
 }
@@ -680,7 +749,7 @@ int launch_slab(const SlabParams& p, int pool, size_t smem, cudaStream_t stream)
 // Returns 1 if the slab kernel was launched, 0 if the shape is not eligible (caller falls back),
 // <0 on a launch error.
 int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W, int C, int pool,
-                    const float* rois, float* top, int* gate, cudaStream_t stream) {
+                    const float* rois, float* top, int* gate, int* sched, cudaStream_t stream) {
   const int hw = H * W;
   if (hw % 4 != 0 || C % 8 != 0 || H < 2 || W < 2) return 0;
   if ((reinterpret_cast<uintptr_t>(bottom) & 15) != 0) return 0;
@@ -690,7 +759,7 @@ int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W
   while (hwp % 32 != 8) hwp += 4;
   const bool small_map = W == 14 && hwp == 200 && C % 32 == 0;  // 14x14: 16-channel passes (CPL 4)
   const size_t staging = (size_t)kConsWarps * 4 * (small_map ? 4 : 2) * kOut * kOut * sizeof(float);
-  const size_t fixed = sizeof(RoiEntry) * kMaxRoiTable + sizeof(int) * kMaxRoiTable +
+  const size_t fixed = sizeof(RoiEntry) * kTabCap + sizeof(int) * 2 * kTabCap +
                        sizeof(uint64_t) * 2 * kStagesMax + staging + 128;
   const size_t budget = (size_t)smem_optin_limit() - 1024;  // static smem + slack
   int cg = 0, stages = 0;
@@ -699,6 +768,7 @@ int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W
     if (C % cand) continue;
     const size_t stage_bytes = (size_t)cand * hwp * 4;
     if (stage_bytes > 64 * 1024 && cand > 8) continue;
+    if (budget < fixed + stage_bytes) continue;
     int st = (int)((budget - fixed) / stage_bytes);
     if (st > kStagesMax) st = kStagesMax;
     if (st >= 2) {
@@ -726,6 +796,7 @@ int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W
   p.stages = stages;
   p.units = B * p.groups;
   p.gate = gate;
+  p.sched = sched;
   const size_t smem = (size_t)cg * hwp * 4 * stages + fixed;
   if (W == 50 && hwp == 1928 && cg == 8) return launch_slab<50, 1928, 2, 1>(p, pool, smem, stream);  // 38x50
   if (small_map && cg == 32) return launch_slab<14, 200, 4, 2>(p, pool, smem, stream);                // 14x14
@@ -747,13 +818,12 @@ using namespace nafae;
 
 NAFAE_CTA_TRACE_READER(nafae_debug_cta_trace_roi_align)
 
-NAFAE_API int nafae_roi_align_persistent_ctas(int num_units) { return slab_grid(num_units); }
+NAFAE_API int nafae_roi_align_persistent_ctas(int num_units) { return slab_grid(num_units, true); }
 
 NAFAE_API size_t nafae_roi_align_workspace_bytes(int batch_size, int num_rois) {
-  (void)batch_size;
   (void)num_rois;
-  // optional: the residency gate (the RoI tables live in shared memory)
-  return NAFAE_ROI_ALIGN_WS_BYTES;
+  // the residency gate + one claim counter per frame (the RoI tables live in shared memory)
+  return align_up((size_t)NAFAE_ROI_ALIGN_WS_BYTES + sizeof(int) * (size_t)(batch_size > 0 ? batch_size : 0), 64);
 }
 
 NAFAE_API int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size,
@@ -765,7 +835,13 @@ NAFAE_API int nafae_roi_align_forward(const float* bottom_data, float spatial_sc
   NAFAE_REQUIRE(workspace == nullptr || workspace_bytes == 0 ||
                     workspace_bytes >= NAFAE_ROI_ALIGN_WS_BYTES,
                 "roi_align: workspace must be NULL or >= %d bytes", NAFAE_ROI_ALIGN_WS_BYTES);
-  int* gate = workspace != nullptr && workspace_bytes > 0 ? static_cast<int*>(workspace) : nullptr;
+  int* ws = workspace != nullptr && workspace_bytes > 0 ? static_cast<int*>(workspace) : nullptr;
+  int* gate = (flags & NAFAE_FLAG_NO_GATE) ? nullptr : ws;
+  // dynamic unit scheduling needs the per-frame claim counters behind the gate words
+  int* sched = ws != nullptr && workspace_bytes >= nafae_roi_align_workspace_bytes(batch_size, num_rois) &&
+                       (reinterpret_cast<uintptr_t>(workspace) & 3) == 0
+                   ? ws + kWsSched
+                   : nullptr;
   NAFAE_REQUIRE(batch_size >= 0 && num_rois >= 0 && channels >= 0, "roi_align: negative sizes");
   NAFAE_REQUIRE(pool_mode >= NAFAE_POOL_NONE && pool_mode <= NAFAE_POOL_MAX,
                 "roi_align: bad pool_mode %d", pool_mode);
@@ -782,7 +858,7 @@ NAFAE_API int nafae_roi_align_forward(const float* bottom_data, float spatial_sc
   if (!exact && pool_mode != NAFAE_POOL_NONE && out_height == kOut && out_width == kOut &&
       batch_size > 0) {
     const int st = try_launch_slab(bottom_data, spatial_scale, batch_size, num_rois, height, width,
-                                   channels, pool_mode, bottom_rois, top_data, gate, stream);
+                                   channels, pool_mode, bottom_rois, top_data, gate, sched, stream);
     if (st != 0) return st;
   }
   if (gate) gate_open(gate, stream);  // no persistent kernel on this path: nothing to wait for

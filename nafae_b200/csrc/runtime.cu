@@ -73,6 +73,21 @@ __global__ void gate_sync_kernel(int* gate) {
   if (threadIdx.x < 6) gate[2 + threadIdx.x] = gate[1];
 }
 
+// diagnostics: CTAs that hold `smem` bytes of shared memory (i.e. a whole SM each when large) and
+// spin for a fixed wall time -- lets a test squeeze the other kernels onto the few remaining SMs
+__global__ void occupy_kernel(unsigned long long ns) {
+  extern __shared__ unsigned char occupy_smem[];
+  if (threadIdx.x == 0) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    occupy_smem[0] = 1;
+    do {
+      __nanosleep(1000);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
+  }
+}
+
 void gate_open(void* gate, cudaStream_t stream) {
   gate_open_kernel<<<1, 32, 0, stream>>>(static_cast<int*>(gate));
 }
@@ -85,6 +100,23 @@ NAFAE_API int nafae_gate_wait(void* gate, int slot, cudaStream_t stream) {
   NAFAE_REQUIRE(gate != nullptr && slot >= 0 && slot < 6, "gate_wait: bad gate/slot");
   nafae::gate_wait_kernel<<<1, 32, 0, stream>>>(static_cast<int*>(gate), slot);
   return nafae::launch_status("gate_wait_kernel");
+}
+
+NAFAE_API int nafae_debug_occupy_sms(int num_ctas, int smem_bytes, unsigned long long nanoseconds,
+                                     cudaStream_t stream) {
+  NAFAE_REQUIRE(num_ctas >= 1 && num_ctas <= 1024 && smem_bytes >= 0 && smem_bytes <= 227 * 1024 &&
+                    nanoseconds <= 2000000000ull,
+                "debug_occupy: bad arguments (at most 1024 CTAs, 227 KB, 2 s)");
+  if (smem_bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nafae::occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes);
+    if (e != cudaSuccess) {
+      nafae::set_error("debug_occupy: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return -(int)e;
+    }
+  }
+  nafae::occupy_kernel<<<num_ctas, 32, smem_bytes, stream>>>(nanoseconds);
+  return nafae::launch_status("occupy_kernel");
 }
 
 NAFAE_API int nafae_gate_sync(void* gate, cudaStream_t stream) {

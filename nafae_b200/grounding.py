@@ -16,7 +16,7 @@ from . import _C
 
 class _Ground(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, vis_feats, word_feats, lens, dims, Delta, vis_lam, train, pool):
+    def forward(ctx, vis_feats, word_feats, lens, dims, Delta, vis_lam, train, pool, recording):
         Na, Ns, Nb, Ne, D = dims
         vis = _C.f32c(vis_feats, "vis_feats")
         word = _C.f32c(word_feats, "word_feats")
@@ -35,9 +35,11 @@ class _Ground(torch.autograd.Function):
                                              _C.ptr(D_ind), _C.ptr(D_sim), _C.ptr(loss),
                                              _C.ptr(ws), ws.numel() * 4, _C.stream(dev))
         _C.check(st, "nafae_ground_forward")
-        # a backward can only follow when a graph is being recorded (not under torch.no_grad(), the
-        # usual validation loop over live modules): otherwise the workspace goes straight back
-        needs_bwd = torch.is_grad_enabled() and (vis_feats.requires_grad or word_feats.requires_grad)
+        # a backward can only follow when a graph is being recorded (`recording` = the caller's
+        # torch.is_grad_enabled(); inside Function.forward grad mode is always off): under
+        # torch.no_grad() -- the usual validation loop over live modules -- the workspace goes
+        # straight back to the pool
+        needs_bwd = recording and (vis_feats.requires_grad or word_feats.requires_grad)
         ctx.cfg = (dims, float(Delta), float(vis_lam), int(train))
         ctx.pool = pool
         if needs_bwd:
@@ -71,7 +73,7 @@ class _Ground(torch.autograd.Function):
         _C.check(st, "nafae_ground_backward")
         ctx.pool.give((Na, Ns, Nb, Ne, D), dev, ws)
         ctx.ws = None
-        return gvis, gword, None, None, None, None, None, None
+        return gvis, gword, None, None, None, None, None, None, None
 
 
 class _WorkspacePool(object):
@@ -108,7 +110,7 @@ def ground(vis_feats, word_feats, entities_length, Na, Nb, Ne, Delta, vis_lam, t
     if lens.numel() != Na:
         raise ValueError("entities_length must have Na=%d entries" % Na)
     return _Ground.apply(vis_feats, word_feats, lens, dims, Delta, vis_lam, train,
-                         pool if pool is not None else _DEFAULT_POOL)
+                         pool if pool is not None else _DEFAULT_POOL, torch.is_grad_enabled())
 
 
 _DEFAULT_POOL = _WorkspacePool()

@@ -51,7 +51,9 @@ class GroundingStep(object):
         nbytes = int(_C.lib.nafae_ground_workspace_bytes(*self.dims))
         self.ws = torch.zeros((nbytes // 4,), dtype=torch.int32, device=self.dev)
         # RoIAlign workspace: the persistent kernel's residency gate (include/nafae_b200.h)
-        self.gate = torch.zeros((_C.ROI_ALIGN_WS_BYTES // 4,), dtype=torch.int32, device=self.dev)
+        # + one claim counter per frame (dynamic unit scheduling)
+        self.align_ws_bytes = int(_C.lib.nafae_roi_align_workspace_bytes(self.F, self.R))
+        self.gate = torch.zeros((self.align_ws_bytes // 4,), dtype=torch.int32, device=self.dev)
         self.graph = None
 
     # -- input staging ---------------------------------------------------------------------
@@ -93,8 +95,8 @@ class GroundingStep(object):
         with torch.cuda.device(self.dev):
             _C.check(L.nafae_roi_align_forward(P(self.features), self.scale, self.F, self.R, self.H,
                                                self.W, self.C, 7, 7, _C.POOL_AVG, P(self.rois),
-                                               P(self.pooled), 0, P(self.gate) if gated else None,
-                                               _C.ROI_ALIGN_WS_BYTES if gated else 0, _C.stream(self.dev)),
+                                               P(self.pooled), 0 if gated else _C.FLAG_NO_GATE,
+                                               P(self.gate), self.align_ws_bytes, _C.stream(self.dev)),
                      "nafae_roi_align_forward")
 
     def sync_gate(self):

@@ -138,3 +138,25 @@ def test_repeated_steps_reuse_workspace_cleanly():
         np.testing.assert_array_equal(again[0], first[0])
         assert again[2] == first[2]
         np.testing.assert_allclose(again[3], first[3], rtol=1e-5, atol=1e-7)
+
+
+@gpu
+def test_no_grad_forward_returns_the_workspace_and_second_backward_is_a_clear_error():
+    """under torch.no_grad() with requires-grad inputs (validation over live modules) the
+    forward must not keep the workspace for a backward that never comes; a second backward through
+    one forward (retain_graph) raises instead of passing a NULL workspace."""
+    import torch
+    from nafae_b200.grounding import _WorkspacePool, ground
+    dev = torch.device("cuda:0")
+    pool = _WorkspacePool()
+    vis = torch.randn(2 * 3 * 4, 64, device=dev, requires_grad=True)
+    word = torch.randn(2 * 5, 64, device=dev, requires_grad=True)
+    with torch.no_grad():
+        for _ in range(3):
+            ground(vis, word, [2, 3], 2, 4, 5, 10.0, 1.0, False, pool)
+    assert sum(len(v) for v in pool._free.values()) == 1  # one workspace, recycled every time
+    D_ind, D_sim, loss = ground(vis, word, [2, 3], 2, 4, 5, 10.0, 1.0, True, pool)
+    loss.backward(retain_graph=True)
+    assert vis.grad is not None and sum(len(v) for v in pool._free.values()) == 1
+    with pytest.raises(RuntimeError, match="second backward"):
+        loss.backward()

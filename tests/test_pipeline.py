@@ -276,3 +276,40 @@ def test_l1_loss_sign_comes_from_the_forward_workspace():
         outs.append((st.grad_word.clone(), st.grad_vis.clone()))
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-7)  # clustering atomics: order
+
+
+def _raw_stream(s):
+    import ctypes
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+@gpu
+@pytest.mark.timeout(200, method="thread")
+def test_head_and_roi_align_make_progress_on_two_free_sms():
+    """Forward progress is not left to convention: with all but TWO SMs held by resident CTAs, the
+    kernels whose CTAs wait on other CTAs of the same launch (ground_fwd's phase chain, ground_bwd's
+    clustering CTAs behind block 0, the RoIAlign kernel's producer / consumer rings and its dynamic
+    claiming) still finish, repeatedly, with the same results."""
+    import time
+    from nafae_b200 import _C
+    c, b, st = _step("cfg2", 21)
+    st.run()
+    torch.cuda.synchronize()
+    want = [t.clone() for t in (st.pooled, st.D_ind, st.D_sim, st.loss, st.grad_word)]
+    gv = st.grad_vis.clone()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    side = torch.cuda.Stream()
+    # warm the occupy kernel (module load) before anything spins
+    assert _C.lib.nafae_debug_occupy_sms(1, 200 * 1024, 1000, _C.stream()) == 1
+    torch.cuda.synchronize()
+    for rounds in range(2):
+        assert _C.lib.nafae_debug_occupy_sms(sms - 2, 200 * 1024, 400_000_000, _raw_stream(side)) == 1
+        time.sleep(0.02)  # the occupying CTAs are resident now
+        for _ in range(40):
+            st.pooled.zero_()
+            st.run_align()
+            st.run_head()
+        torch.cuda.synchronize()
+        for w, t in zip(want, (st.pooled, st.D_ind, st.D_sim, st.loss, st.grad_word)):
+            assert torch.equal(w, t)
+        assert torch.allclose(gv, st.grad_vis, rtol=1e-5, atol=1e-7)

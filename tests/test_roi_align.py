@@ -244,3 +244,48 @@ def test_reference_named_launchers():
     assert st == 1
     ref = ocpu.roi_align_backward(td.cpu().numpy(), c["rois"], f.shape, c["scale"])
     _close(bd.cpu().numpy(), ref, rtol=1e-5)
+
+
+@gpu
+@pytest.mark.parametrize("name,F,C,H,W,per_frame,shuffle", [
+    ("cfg2_like", 40, 64, 38, 50, [20] * 40, False),
+    ("real_14x14", 40, 64, 14, 14, [20] * 40, False),
+    ("ragged_shuffled_empty_frames", 9, 32, 38, 50, [3, 0, 40, 1, 17, 0, 60, 52, 53], True),
+    ("whole_table_and_chunked", 4, 16, 38, 50, [300, 5, 130, 104], True),
+    ("more_than_1024_rois", 12, 8, 38, 50, [100] * 12, False),
+])
+def test_dynamic_unit_claiming_equals_static_split(name, F, C, H, W, per_frame, shuffle):
+    """With a full workspace the persistent CTAs claim (frame, channel-group) units dynamically;
+    the arithmetic per unit is the same, so the output must be BIT-identical to the static split
+    (no workspace), launch after launch, and the claim counters must be left zeroed."""
+    from nafae_b200 import _C
+    rs = np.random.RandomState(len(name) * 7 + F)
+    feat = _t(synth.conv5_maps(rs, F, C, H, W) - 0.3)
+    rois_np = _frame_rois(rs, F, per_frame, H * 16, W * 16, shuffle)
+    rois = _t(rois_np)
+    R = rois.shape[0]
+
+    def run(ws, flags=0):
+        out = torch.full((R, C, 7, 7), float("nan"), device=_dev())
+        st = _C.lib.nafae_roi_align_forward(_C.ptr(feat), 1 / 16., F, R, H, W, C, 7, 7, _C.POOL_AVG,
+                                            _C.ptr(rois), _C.ptr(out), flags, _C.ptr(ws),
+                                            ws.numel() * 4 if ws is not None else 0, _C.stream())
+        assert st == 1, _C.last_error()
+        return out
+    static = run(None)
+    _close(static.cpu().numpy(), ocpu.roi_align_avg_forward(feat.cpu().numpy(), rois_np, 7, 7, 1 / 16.))
+    nbytes = int(_C.lib.nafae_roi_align_workspace_bytes(F, R))
+    assert nbytes >= 64 + 4 * F
+    ws = torch.zeros(nbytes // 4, dtype=torch.int32, device=_dev())
+    for it in range(3):
+        got = run(ws, _C.FLAG_NO_GATE if it == 1 else 0)
+        torch.cuda.synchronize()
+        assert torch.equal(got, static), (name, it)
+        assert int(ws[16:16 + F].abs().sum()) == 0 and int(ws[8]) == 0 and int(ws[0]) == 0
+    assert int(ws[1]) == 2  # two gated launches opened the gate, the NO_GATE one did not
+    # fewer SMs than units, and a single CTA
+    prev = _C.lib.nafae_set_reserved_sms(140)
+    try:
+        assert torch.equal(run(ws), static)
+    finally:
+        _C.lib.nafae_set_reserved_sms(prev)

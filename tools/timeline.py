@@ -3,7 +3,7 @@ make -C nafae_b200/csrc trace).  Prints, for the last replay, when each kernel's
 ended relative to the first CTA of the replay, and the RoIAlign kernel's own / stolen unit counts."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["NAFAE_B200_LIB"] = os.path.join(ROOT, "nafae_b200", "libnafae_b200_trace.so")
+os.environ["NAFAE_B200_LIB"] = os.path.join(ROOT, "tools", "_build", "libnafae_b200_trace.so")
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from nafae_b200 import synth, _C, parallel
@@ -29,7 +29,8 @@ side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
 comm = torch.cuda.Stream(dev)
 buckets = None
 if world > 1:
-    buckets = [parallel.PeerAllReduce(parallel.trainable_grad_elems(), dev) for _ in range(2)]
+    buckets = [parallel.make_allreduce(parallel.trainable_grad_elems(), dev, kind=os.environ.get("AR_KIND", "auto"))
+               for _ in range(2)]
     for st, b in zip(steps, buckets):
         st.grad_word = b.views([(st.NQ, c["D"])])[0]
         b.launch()
@@ -119,12 +120,12 @@ for (sa, sb) in segs[-2:]:
               % (names[k], len(x), len(np.unique(x["smid"])), t0.min(), np.percentile(t0, 50), np.percentile(t0, 90), t0.max(),
                  t1.min(), np.percentile(t1, 50), np.percentile(t1, 90), t1.max(), np.percentile(t1 - t0, 50), (t1 - t0).max()))
         if k == 1:
-            print("            own units/CTA min %d p50 %d max %d, stolen total %d (by %d CTAs); starters later than 5 us: %d"
-                  % (x["a"].min(), np.percentile(x["a"], 50), x["a"].max(), x["b"].sum(), (x["b"] > 0).sum(), (t0 > 5).sum()))
+            print("            items/CTA min %d p50 %d max %d (total %d), RoI passes/CTA min %d max %d; starters later than 5 us: %d"
+                  % (x["a"].min(), np.percentile(x["a"], 50), x["a"].max(), x["a"].sum(), x["b"].min(), x["b"].max(), (t0 > 5).sum()))
             late = x[t0 > 5]
             if len(late):
                 lt0 = (late["t0"].astype(np.int64) - base) / 1e3
-                print("            late: start p50 %.1f max %.1f, their own units p50 %d" % (np.percentile(lt0, 50), lt0.max(), np.percentile(late["a"], 50)))
+                print("            late: start p50 %.1f max %.1f, their items p50 %d" % (np.percentile(lt0, 50), lt0.max(), np.percentile(late["a"], 50)))
         if k in (3, 4):  # long-lived CTAs of the head kernels: where and when
             long_ = x[(t1 - t0) > 4]
             lt0 = (long_["t0"].astype(np.int64) - base) / 1e3

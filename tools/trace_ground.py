@@ -1,7 +1,7 @@
 """Dev tool: phase timestamps of ground_fwd_kernel (needs libnafae_b200_trace.so, -DNAFAE_TRACE)."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["NAFAE_B200_LIB"] = os.path.join(ROOT, "nafae_b200", "libnafae_b200_trace.so")
+os.environ["NAFAE_B200_LIB"] = os.path.join(ROOT, "tools", "_build", "libnafae_b200_trace.so")
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from nafae_b200 import synth, _C
