@@ -271,6 +271,8 @@ def run_ours(args):
             comm_sms = parallel.COMM_SMS
     reserve = args.reserve_sms if args.reserve_sms >= 0 else (HEAD_SMS if pipelined else 0) + comm_sms
     _C.lib.nafae_set_reserved_sms(reserve)
+    # CTAs of the persistent RoIAlign kernel in the timed loops below (step graphs AND kernel-alone)
+    slab_ctas = int(_C.lib.nafae_roi_align_persistent_ctas(steps[0].F * (c["C"] // 8)))
     side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
     comm = torch.cuda.Stream(dev) if world > 1 else None
     for st, hb in zip(steps, host):
@@ -465,7 +467,7 @@ def run_ours(args):
                 gpu_launches=K * steps[0].kernels_per_step(),
                 roofline=dict(bound="hbm", kernel="align_pool_fwd_slab", achieved=achieved, peak=peak,
                               unit="GB/s", frac=achieved / peak, traffic=traffic,
-                              kernel_us=kern_us, kernel_grid_sms=int(_C.lib.nafae_roi_align_persistent_ctas(steps[0].F * (c["C"] // 8))),
+                              kernel_us=kern_us, kernel_grid_sms=slab_ctas, reserved_sms=reserve,
                               algorithmic_bytes=ab["total"], peak_source=peak_src,
                               step_frac=(ab["total"] / (ms_total / K * 1e-3) / 1e9) / peak),
                 clocks=clocks)
