@@ -204,6 +204,16 @@ int nafae_ground_forward(const float* vis_feats, const float* word_feats,
                          float Delta, float vis_lam, int train, int64_t* D_ind, float* D_sim,
                          float* margin_loss, void* workspace, size_t workspace_bytes,
                          cudaStream_t stream);
+/* `groups` INDEPENDENT batches in one launch (gridDim.y): group g reads vis_feats + g*Na*Ns*Nb*D,
+ * word_feats + g*Na*Ne*D, entities_length + g*Na, and writes D_ind / D_sim + g*(Na*Ns)*(Na*Ne),
+ * margin_loss[g], using workspace + g*nafae_ground_workspace_bytes(...).  The evaluation sweep runs
+ * the reference's batch_size_val = 1 (model.py:514,804) for many segments at once this way: every
+ * segment sees only its own queries, exactly as Na = 1 calls would. */
+int nafae_ground_forward_batched(const float* vis_feats, const float* word_feats,
+                                 const int* entities_length, int groups, int Na, int Ns, int Nb, int Ne,
+                                 int D, float Delta, float vis_lam, int train, int64_t* D_ind,
+                                 float* D_sim, float* margin_loss, void* workspace,
+                                 size_t workspace_bytes, cudaStream_t stream);
 int nafae_ground_backward(const float* grad_margin_loss, const float* vis_feats,
                           const float* word_feats, const int* entities_length, int Na, int Ns,
                           int Nb, int Ne, int D, float Delta, float vis_lam, int train,
@@ -216,6 +226,24 @@ int nafae_ground_backward(const float* grad_margin_loss, const float* vis_feats,
  * out_ind (Na, Ns, Ne) int64, out_sim (Na, Ns, Ne) f32. */
 int nafae_ground_postprocess(const int64_t* D_ind, const float* D_sim, int Na, int Ns, int Nb,
                              int Ne, int64_t* out_ind, float* out_sim, cudaStream_t stream);
+
+/* Evaluation sweep on the device: postprocess (model.py:457-474) + record_det (model.py:477-487) +
+ * box accuracy (lib/datasets/youcook_eval.py:241-336) for `num_segments` independent segments whose
+ * D_ind / D_sim are in the batched Na = 1 layout (num_segments, Ns, Ne) of
+ * nafae_ground_forward_batched.  rois (num_segments*Ns*Nb, 5) as produced by nafae_proposal_tail.
+ * Per slot (segment, frame, entity): out_image_ids = image_id_base + segment*Ns + frame (or -1 for a
+ * padded entity slot e >= entities_length[segment]), out_box_rows = the global box row, out_boxes
+ * (.., 4), out_confs; any of the four may be NULL.  With gt_boxes (num_segments, Ns, Ne, 4) f64 -- ONE
+ * ground-truth box per (image, label), the well-formed annotation case -- and gt_classes
+ * (num_segments, Ne) int32, every real slot adds 1 to class_count[class] and, when
+ * overlap >= gt_thr (the reference's +1 pixel convention and NumPy dtypes), to class_match[class]:
+ * the class_match_count / class_count vectors box_accuracy reduces to macro / micro accuracy.  The
+ * counters accumulate across calls (zero them once). */
+int nafae_eval_record(const int64_t* D_ind, const float* D_sim, const int* entities_length,
+                      const float* rois, int num_segments, int Ns, int Nb, int Ne, int64_t image_id_base,
+                      int64_t* out_image_ids, int64_t* out_box_rows, float* out_boxes, float* out_confs,
+                      const double* gt_boxes, const int* gt_classes, float gt_thr, int num_classes,
+                      int* class_match, int* class_count, cudaStream_t stream);
 
 /* ------------------------------------------------------- step wrapper: clip + Adam ---- */
 

@@ -55,11 +55,17 @@ SIGNATURES = {
     "nafae_ground_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_size_t, c_void_p]),
+    "nafae_ground_forward_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                             c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_size_t, c_void_p]),
     "nafae_ground_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nafae_ground_postprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_void_p]),
+    "nafae_eval_record": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_float, c_int, c_void_p, c_void_p, c_void_p]),
     "nafae_clip_adam_workspace_bytes": (c_size_t, []),
     "nafae_clip_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float,
                                      c_float, c_float, c_float, c_float, c_void_p, c_size_t, c_void_p]),

@@ -136,6 +136,8 @@ struct FwdParams {
   float Delta, vis_lam;
   int train;
   int col_chunks;
+  int groups;            // independent batches (gridDim.y); each has its own inputs, outputs, workspace
+  size_t ws_group_bytes;
 };
 
 // 16 per-lane partial sums -> lanes 2*i and 2*i+1 both hold the warp total of value i.
@@ -167,8 +169,21 @@ __device__ __forceinline__ float reduce16(const float (&v)[16], int lane) {
 __device__ void phase2_segment(const FwdParams& p, const Ws& w, int a);
 __device__ void phase3_final(const FwdParams& p, const Ws& w);
 
-__global__ void __launch_bounds__(kFwdThreads, 1) ground_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) ground_fwd_kernel(const FwdParams p_in) {
   NAFAE_CTA_TRACE(cta_trace, 3);
+  // independent groups (evaluation sweep: Na = 1 per segment, many segments per launch): the group
+  // index only offsets the pointers, everything below is unchanged
+  FwdParams p = p_in;
+  if (p_in.groups > 1) {
+    const size_t g = blockIdx.y;
+    p.vis += g * (size_t)p_in.d.F * p_in.d.Nb * p_in.d.D;
+    p.word += g * (size_t)p_in.d.NQ * p_in.d.D;
+    p.lens += g * (size_t)p_in.d.Na;
+    p.D_ind += g * (size_t)p_in.d.F * p_in.d.NQ;
+    p.D_sim += g * (size_t)p_in.d.F * p_in.d.NQ;
+    p.loss += g;
+    p.ws = static_cast<char*>(p_in.ws) + g * p_in.ws_group_bytes;
+  }
   extern __shared__ __align__(16) float sm[];  // kRowTile * D floats (vis rows of the frame)
   __shared__ int s_ticket;
   __shared__ int s_live[kLiveMax];       // compacted list of live (unmasked) columns
@@ -1054,6 +1069,57 @@ __global__ void postprocess_kernel(const long long* __restrict__ D_ind,
   }
 }
 
+// Evaluation sweep, one thread per (segment g, frame s, entity slot e) of `G` independent segments
+// (D_ind / D_sim in the batched Na = 1 layout (G, Ns, Ne)):
+//   model.py:457-474 postprocess : global box row (g*Ns + s)*Nb + D_ind
+//   model.py:477-487 record_det  : box / confidence / image id of every real entity (e < len[g])
+//   youcook_eval.py:241-336      : box accuracy against ONE ground-truth box per (image, label) --
+//        overlap with the +1 pixel convention in float64, detection area in the boxes' own fp32
+//        (the dtypes NumPy uses there, :206-221), hit when overlap >= thr; per-class counters
+// Slots e >= len[g] are written as invalid (image id -1).
+__global__ void eval_record_kernel(const long long* __restrict__ D_ind, const float* __restrict__ D_sim,
+                                   const int* __restrict__ lens, const float* __restrict__ rois, int G,
+                                   int Ns, int Nb, int Ne, long long img_base,
+                                   long long* __restrict__ out_img, long long* __restrict__ out_row,
+                                   float* __restrict__ out_box, float* __restrict__ out_conf,
+                                   const double* __restrict__ gt_box, const int* __restrict__ gt_cls,
+                                   float gt_thr, int n_cls, int* __restrict__ class_match,
+                                   int* __restrict__ class_count) {
+  const int n = G * Ns * Ne;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int e = i % Ne, s = (i / Ne) % Ns, g = i / (Ne * Ns);
+    const bool live = e < __ldg(lens + g);
+    const long long row = (long long)(g * Ns + s) * Nb + (live ? D_ind[i] : 0);
+    const float* r = rois + row * 5;
+    const float x1 = r[1], y1 = r[2], x2 = r[3], y2 = r[4];
+    if (out_img) out_img[i] = live ? img_base + (long long)g * Ns + s : -1;
+    if (out_row) out_row[i] = live ? row : -1;
+    if (out_box) {
+      out_box[(size_t)i * 4 + 0] = live ? x1 : 0.f;
+      out_box[(size_t)i * 4 + 1] = live ? y1 : 0.f;
+      out_box[(size_t)i * 4 + 2] = live ? x2 : 0.f;
+      out_box[(size_t)i * 4 + 3] = live ? y2 : 0.f;
+    }
+    if (out_conf) out_conf[i] = live ? D_sim[i] : 0.f;
+    if (gt_box != nullptr && live) {
+      const int cls = __ldg(gt_cls + g * Ne + e);
+      if (cls >= 0 && cls < n_cls) {
+        const double* gb = gt_box + (size_t)i * 4;
+        const double left = fmax((double)x1, gb[0]), top = fmax((double)y1, gb[1]);
+        const double right = fmin((double)x2, gb[2]), bottom = fmin((double)y2, gb[3]);
+        const double iw = __dadd_rn(__dsub_rn(right, left), 1.), ih = __dadd_rn(__dsub_rn(bottom, top), 1.);
+        const float darea = __fmul_rn(__fadd_rn(__fsub_rn(x2, x1), 1.f), __fadd_rn(__fsub_rn(y2, y1), 1.f));
+        const double garea = __dmul_rn(__dadd_rn(__dsub_rn(gb[2], gb[0]), 1.), __dadd_rn(__dsub_rn(gb[3], gb[1]), 1.));
+        const double inter = __dmul_rn(iw, ih);
+        const double uni = __dsub_rn(__dadd_rn((double)darea, garea), inter);
+        const bool hit = iw > 0. && ih > 0. && __ddiv_rn(inter, uni) >= (double)gt_thr;
+        atomicAdd(class_count + cls, 1);
+        if (hit) atomicAdd(class_match + cls, 1);
+      }
+    }
+  }
+}
+
 bool make_dims(int Na, int Ns, int Nb, int Ne, int D, Dims* d) {
   if (Na <= 0 || Ns <= 0 || Nb <= 0 || Ne <= 0 || D <= 0) return false;
   d->Na = Na;
@@ -1102,9 +1168,24 @@ NAFAE_API int nafae_ground_forward(const float* vis_feats, const float* word_fea
                                    int D, float Delta, float vis_lam, int train, int64_t* D_ind,
                                    float* D_sim, float* margin_loss, void* workspace,
                                    size_t workspace_bytes, cudaStream_t stream) {
+  return nafae_ground_forward_batched(vis_feats, word_feats, entities_length, 1, Na, Ns, Nb, Ne, D, Delta,
+                                      vis_lam, train, D_ind, D_sim, margin_loss, workspace,
+                                      workspace_bytes, stream);
+}
+
+NAFAE_API int nafae_ground_forward_batched(const float* vis_feats, const float* word_feats,
+                                           const int* entities_length, int groups, int Na, int Ns,
+                                           int Nb, int Ne, int D, float Delta, float vis_lam, int train,
+                                           int64_t* D_ind, float* D_sim, float* margin_loss,
+                                           void* workspace, size_t workspace_bytes,
+                                           cudaStream_t stream) {
   Dims d;
   NAFAE_REQUIRE(make_dims(Na, Ns, Nb, Ne, D, &d), "ground: sizes must be positive");
-  if (check_ground_args(d, workspace, workspace_bytes, train) != 1) return 0;
+  NAFAE_REQUIRE(groups >= 1 && groups <= 65535, "ground: groups must be in [1, 65535]");
+  const size_t ws_group = nafae_ground_workspace_bytes(Na, Ns, Nb, Ne, D);
+  NAFAE_REQUIRE(workspace_bytes / (size_t)groups >= ws_group, "ground: workspace too small for %d groups",
+                groups);
+  if (check_ground_args(d, workspace, ws_group, train) != 1) return 0;
   NAFAE_REQUIRE(vis_feats && word_feats && entities_length && D_ind && D_sim && margin_loss,
                 "ground: NULL buffer");
   NAFAE_REQUIRE((reinterpret_cast<uintptr_t>(vis_feats) & 15) == 0,
@@ -1122,8 +1203,10 @@ NAFAE_API int nafae_ground_forward(const float* vis_feats, const float* word_fea
   p.vis_lam = vis_lam;
   p.train = train ? 1 : 0;
   // CTAs per frame: enough to fill the GPU once, never more than the column chunks there can be
+  p.groups = groups;
+  p.ws_group_bytes = ws_group;
   {
-    int g = ceil_div(sm_count(), d.F);
+    int g = ceil_div(sm_count(), d.F * groups);
     const int gmax = ceil_div(d.NQ, kColsPerCta);
     p.col_chunks = g < 1 ? 1 : (g > gmax ? gmax : g);
   }
@@ -1144,7 +1227,7 @@ NAFAE_API int nafae_ground_forward(const float* vis_feats, const float* word_fea
       return -(int)e;
     }
   }
-  ground_fwd_kernel<<<d.F * p.col_chunks, kFwdThreads, smem, stream>>>(p);
+  ground_fwd_kernel<<<dim3(d.F * p.col_chunks, groups), kFwdThreads, smem, stream>>>(p);
   return launch_status("ground_fwd_kernel");
 }
 
@@ -1203,4 +1286,26 @@ NAFAE_API int nafae_ground_postprocess(const int64_t* D_ind, const float* D_sim,
       reinterpret_cast<const long long*>(D_ind), D_sim, Na, Ns, Nb, Ne,
       reinterpret_cast<long long*>(out_ind), out_sim);
   return launch_status("postprocess_kernel");
+}
+
+NAFAE_API int nafae_eval_record(const int64_t* D_ind, const float* D_sim, const int* entities_length,
+                                const float* rois, int num_segments, int Ns, int Nb, int Ne,
+                                int64_t image_id_base, int64_t* out_image_ids, int64_t* out_box_rows,
+                                float* out_boxes, float* out_confs, const double* gt_boxes,
+                                const int* gt_classes, float gt_thr, int num_classes, int* class_match,
+                                int* class_count, cudaStream_t stream) {
+  NAFAE_REQUIRE(num_segments > 0 && Ns > 0 && Nb > 0 && Ne > 0, "eval_record: sizes must be positive");
+  NAFAE_REQUIRE(D_ind && D_sim && entities_length && rois, "eval_record: NULL input");
+  NAFAE_REQUIRE((long long)num_segments * Ns * Ne < (1ll << 31), "eval_record: too many slots");
+  NAFAE_REQUIRE(gt_boxes == nullptr || (gt_classes && class_match && class_count && num_classes > 0),
+                "eval_record: ground truth needs gt_classes, class_match, class_count, num_classes");
+  const int n = num_segments * Ns * Ne;
+  int grid = ceil_div(n, 256);
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
+  eval_record_kernel<<<grid, 256, 0, stream>>>(
+      reinterpret_cast<const long long*>(D_ind), D_sim, entities_length, rois, num_segments, Ns, Nb, Ne,
+      (long long)image_id_base, reinterpret_cast<long long*>(out_image_ids),
+      reinterpret_cast<long long*>(out_box_rows), out_boxes, out_confs, gt_boxes, gt_classes, gt_thr,
+      num_classes, class_match, class_count);
+  return launch_status("eval_record_kernel");
 }

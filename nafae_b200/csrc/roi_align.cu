@@ -271,6 +271,10 @@ constexpr int kTabCap = 104;        // RoI table entries in shared memory
 constexpr int kTabHalf = kTabCap / 2;
 constexpr int kStagesMax = 4;
 constexpr int kFrRegs = 32;         // frame ids cached per producer lane (R <= 1024)
+#ifndef NAFAE_SLAB_SCAV_DEPTH
+#define NAFAE_SLAB_SCAV_DEPTH 2
+#endif
+constexpr int kScavDepth = NAFAE_SLAB_SCAV_DEPTH;  // items in the ring while scavenging other frames
 // workspace words (ints): [0] residency arrivals, [1] gate epoch, [2..7] epochs seen per waiting slot,
 // [8] exit ticket, [16 + f] claim counter of frame f
 constexpr int kWsExit = 8;
@@ -368,8 +372,6 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
     int cur_f = (int)((long long)p.B * blockIdx.x / gridDim.x);       // dynamic: frame being drained
     int u_next = (int)((long long)p.units * blockIdx.x / gridDim.x);  // static: contiguous range
     const int u_end = (int)((long long)p.units * (blockIdx.x + 1) / gridDim.x);
-    const int share = p.units / (int)gridDim.x;  // expected units per CTA
-    int claimed = 0;
     int it = 0;                     // items published so far
     int half_f[2] = {-1, -1};       // frame whose complete table sits in half h (-2: part of a whole-buffer table)
     int half_n[2] = {0, 0};
@@ -460,18 +462,22 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
       }
       __syncwarp();
     };
-    // next unit of this CTA, -1 when there is none (warp-uniform)
-    auto claim = [&]() -> int {
-      if (!dynamic) return u_next < u_end ? u_next++ : -1;
+    // Dynamic claiming.  OWN mode: the CTA drains the frame it was dealt (cur_f) -- the atomic for
+    // the NEXT unit is issued right after an item is published and its result is only read after the
+    // wait for a free stage, so its L2 round trip never delays a bulk copy.  When the frame runs
+    // dry the CTA SCAVENGES the nearest frame that still has unclaimed units, one synchronous claim
+    // at a time and only one unit ahead of the one being processed, so that no CTA sits on claimed
+    // work while others are idle at the tail; a frame with plenty left is adopted (back to OWN).
+    int pend = 0;            // lane 0: result of the claim in flight (OWN mode)
+    bool scavenging = false;
+    auto start_claim = [&]() {
+      if (lane == 0) pend = atomicAdd(p.sched + cur_f, 1);
+    };
+    auto scavenge = [&]() -> int {  // -1: no work left anywhere
       while (cur_f >= 0) {
-        int g = 0;
-        if (lane == 0) g = atomicAdd(p.sched + cur_f, 1);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        if (g < p.groups) return cur_f * p.groups + g;
-        // this frame is fully claimed: nearest frame (cyclically) that still has unclaimed units
         int found = -1;
-        for (int base = 1; base < p.B && found < 0; base += 32) {
-          const int k = base + lane;
+        for (int base = 0; base < p.B && found < 0; base += 32) {
+          const int k = base + lane;  // distance from cur_f (0: cur_f itself)
           int f = cur_f + k;
           if (f >= p.B) f -= p.B;
           const bool open = k < p.B && __ldcg(p.sched + f) < p.groups;
@@ -482,8 +488,26 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
           }
         }
         cur_f = found;
+        if (found < 0) break;
+        int g = 0;
+        if (lane == 0) g = atomicAdd(p.sched + found, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g < p.groups) {
+          if (g + 8 < p.groups) scavenging = false;  // plenty left: adopt this frame
+          return found * p.groups + g;
+        }
       }
       return -1;
+    };
+    // next unit of this CTA, -1 when there is none (warp-uniform)
+    auto claim = [&]() -> int {
+      if (!dynamic) return u_next < u_end ? u_next++ : -1;
+      if (!scavenging) {
+        const int g = __shfl_sync(0xffffffffu, pend, 0);
+        if (g < p.groups) return cur_f * p.groups + g;
+        scavenging = true;
+      }
+      return scavenge();
     };
     // publish one item: slab of unit (f, gidx) + table range [j0, j0+n)
     auto issue_slab = [&](int f, int gidx) {
@@ -506,14 +530,15 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
       ++it;
     };
 
+    if (dynamic) start_claim();  // in flight while the frame ids load
     for (;;) {
-      // room for one more item?  normally `stages` deep; near the end of the expected share only
-      // one unit ahead of the one being processed, so that no CTA sits on claimed work at the tail
-      const int depth = (!dynamic || claimed < share - 2) ? p.stages : (p.stages < 2 ? p.stages : 2);
+      // room for one more item?  `stages` deep while draining the own frame, one unit ahead of the
+      // one being processed while scavenging
+      const int depth = (!dynamic || !scavenging) ? p.stages : (p.stages < kScavDepth ? p.stages : kScavDepth);
       wait_released(it - depth);
       const int u = claim();
       if (u < 0) break;
-      ++claimed;
+      if (dynamic && !scavenging) start_claim();  // the next one: hidden behind this item's work
       const int f = u / p.groups, gidx = u - f * p.groups;
       if (f == empty_f) continue;
       int h = half_f[0] == f ? 0 : (half_f[1] == f ? 1 : -1);
