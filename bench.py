@@ -37,7 +37,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cfg", default="cfg2", choices=["cfg2", "cfg2_real", "cfg4"])
+    ap.add_argument("--cfg", default="cfg2", choices=["cfg2", "cfg2_real", "cfg4", "cfg5"])
+    ap.add_argument("--segments", type=int, default=0, help="cfg5: segments in the sweep (default 10000)")
+    ap.add_argument("--check-segments", type=int, default=64,
+                    help="cfg5: segments per rank re-computed with the oracle after the timed sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true",
@@ -517,10 +520,196 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------- cfg5: inference sweep ----
+def run_sweep(args):
+    """BASELINE.json configs[4]: 10 000 synthetic cfg1-shaped segments (eval phase, batch_size_val = 1,
+    reference model.py:800-991), sharded contiguously over the ranks; every rank grounds its shard
+    G segments per launch set (EvalStep), records detections and box-accuracy counters on the
+    device, and the per-class counters are summed over the ranks.  After the timed sweep a sample of
+    segments per rank is recomputed with the oracle (picks and recorded boxes bit-exact) and the
+    device-side accuracy is compared with the host evaluation of the same detections."""
+    import torch
+    import torch.distributed as dist
+    from nafae_b200 import synth, parallel, evaluate
+    from nafae_b200.sweep import EvalStep, accuracy_from_counts, dets_from_records
+
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    rank, world, local = parallel.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    c = dict(synth.CONFIGS["cfg5"])
+    if args.segments > 0:
+        c["segments"] = args.segments
+    S, G, Ns, Nb, Ne, D, P = c["segments"], c["G"], c["Ns"], c["Nb"], c["Ne"], c["D"], c["pool"]
+    begin, end = parallel.shard_segments(S, rank, world)
+    S_r = end - begin
+    n_steps = (S_r + G - 1) // G
+    S_pad = n_steps * G
+    pool = synth.sweep_pool(c)
+    # --- resident inputs.  Per-segment embeddings are generated for the WHOLE sweep from one seed and
+    # sliced, so that every world size grounds the same 10 000 segments.
+    gen = torch.Generator(device=dev).manual_seed(20260)
+    vis = torch.empty((S_pad * Ns * Nb, D), dtype=torch.float32, device=dev)
+    word = torch.empty((S_pad * Ne, D), dtype=torch.float32, device=dev)
+    chunk = 500
+    for s0 in range(0, S, chunk):  # bounded transient memory
+        s1 = min(S, s0 + chunk)
+        v = (torch.randn(((s1 - s0) * Ns * Nb, D), generator=gen, device=dev) * 0.5).clamp_(-1, 1)
+        w = (torch.randn(((s1 - s0) * Ne, D), generator=gen, device=dev) * 0.5).clamp_(-1, 1)
+        lo, hi = max(s0, begin), min(s1, end)
+        if lo < hi:
+            vis[(lo - begin) * Ns * Nb:(hi - begin) * Ns * Nb] = v[(lo - s0) * Ns * Nb:(hi - s0) * Ns * Nb]
+            word[(lo - begin) * Ne:(hi - begin) * Ne] = w[(lo - s0) * Ne:(hi - s0) * Ne]
+    if S_pad > S_r:
+        vis[S_r * Ns * Nb:].zero_()
+        word[S_r * Ne:].zero_()
+    lens = torch.zeros((S_pad,), dtype=torch.int32, device=dev)
+    lens[:S_r] = torch.from_numpy(pool["lens"][begin:end]).to(dev)
+    gt_cls = torch.full((S_pad, Ne), -1, dtype=torch.int32, device=dev)
+    gt_cls[:S_r] = torch.from_numpy(pool["classes"][begin:end]).to(dev)
+    gt_box = torch.zeros((S_pad, Ns, Ne, 4), dtype=torch.float64, device=dev)
+    gt_box[:S_r] = torch.from_numpy(pool["gt_boxes"][begin:end]).to(dev)
+    # proposals: segment s uses pool entry s % P; a launch set of G consecutive segments is a contiguous
+    # slice of the pool laid out twice (begin is not a multiple of G in general)
+    props2 = torch.from_numpy(pool["proposals"]).to(dev).repeat(2, 1, 1, 1)   # (2P, Ns, n, 4)
+    scores2 = torch.from_numpy(pool["scores"]).to(dev).repeat(2, 1, 1)
+    feats = [torch.from_numpy(synth.conv5_maps(np.random.RandomState(77 + i), G * Ns, c["C"], c["H"], c["W"])).to(dev)
+             for i in range(2)]
+    out = dict(image_ids=torch.empty((S_pad, Ns, Ne), dtype=torch.int64, device=dev),
+               box_rows=torch.empty((S_pad, Ns, Ne), dtype=torch.int64, device=dev),
+               boxes=torch.empty((S_pad, Ns, Ne, 4), dtype=torch.float32, device=dev),
+               confs=torch.empty((S_pad, Ns, Ne), dtype=torch.float32, device=dev))
+    picks = torch.empty((S_pad, Ns, Ne), dtype=torch.int64, device=dev)
+    counts = torch.zeros((2, c["classes"]), dtype=torch.int32, device=dev)
+    es = EvalStep(G, Ns, Nb, Ne, D, c["C"], c["H"], c["W"], c["n"], c["classes"], pre_nms_topn=c["pre"],
+                  Delta=c["Delta"], vis_lam=c["vis_lam"], device=dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+
+    def sweep(record_picks):
+        counts.zero_()
+        for k in range(n_steps):
+            a, b = k * G, (k + 1) * G
+            p0 = (begin + a) % P
+            es.run(feats[k & 1], props2[p0:p0 + G].reshape(G * Ns, c["n"], 4),
+                   scores2[p0:p0 + G].reshape(G * Ns, c["n"]), vis[a * Ns * Nb:b * Ns * Nb],
+                   word[a * Ne:b * Ne], lens[a:b], (begin + a) * Ns,
+                   out={kk: v[a:b] for kk, v in out.items()}, gt_boxes=gt_box[a:b], gt_classes=gt_cls[a:b],
+                   class_match=counts[0], class_count=counts[1])
+            if record_picks:
+                picks[a:b].copy_(es.D_ind)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    Wm = max(args.warmup, 3)
+    for _ in range(min(Wm, 3)):
+        sweep(False)  # whole-shard warm-up passes (a "step" of this config is one launch set of G segments)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.1)
+    sweep(False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sweep(False)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if sampler else None
+    sweep(True)  # untimed pass that also keeps the picks for the parity checks
+    torch.cuda.synchronize()
+
+    # ---- parity: oracle on a sample of this rank's segments (checker only; outside the timing)
+    from oracle import cpu as ocpu
+    from oracle import dvsa as odvsa
+    from oracle import eval as oeval
+    nchk = min(args.check_segments, S_r)
+    rs = np.random.RandomState(99 + rank)
+    sample = sorted(rs.choice(S_r, nchk, replace=False).tolist())
+    ok_picks = ok_boxes = True
+    for j in sample:
+        sg = begin + j
+        n_q = int(pool["lens"][sg])
+        o_rois, _, _ = ocpu.proposal_tail(pool["proposals"][sg % P], pool["scores"][sg % P], c["pre"], Nb, 0.7)
+        v = vis[j * Ns * Nb:(j + 1) * Ns * Nb].cpu()
+        w = word[j * Ne:(j + 1) * Ne].cpu()
+        o_ind, o_sim, _, _ = odvsa.dvsa_forward(v, w, [n_q], 1, Nb, Ne, c["Delta"], c["vis_lam"], "eval")
+        oD, _ = odvsa.postprocess(o_ind.numpy(), o_sim.numpy(), 1, Ns, Nb, Ne)
+        got_ind = picks[j].cpu().numpy()
+        ok_picks &= bool(np.array_equal(got_ind[:, :n_q], o_ind.numpy().reshape(Ns, Ne)[:, :n_q]))
+        want_boxes = o_rois.reshape(-1, 5)[:, 1:][oD[0][:, :n_q]]
+        ok_boxes &= bool(np.array_equal(out["boxes"][j].cpu().numpy()[:, :n_q], want_boxes))
+    # ---- accuracy: device counters vs the host evaluation of the same detections
+    classes = ["c%02d" % i for i in range(c["classes"])]
+    cls_np = pool["classes"][begin:end]
+    local_ids = out["image_ids"][:S_r].clone()
+    local_ids[local_ids >= 0] -= begin * Ns
+    dets = dets_from_records(local_ids, out["boxes"][:S_r], out["confs"][:S_r],
+                             lambda sg, e: classes[int(cls_np[sg, e])])
+    recs = []
+    gt_np = pool["gt_boxes"][begin:end]
+    for sg in range(S_r):
+        n_q = int(pool["lens"][begin + sg])
+        for f in range(Ns):
+            recs.append(dict(label=[classes[int(cls_np[sg, e])] for e in range(n_q)],
+                             bbox=[gt_np[sg, f, e] for e in range(n_q)], thr=[0.5] * n_q))
+    host_box = evaluate.box_accuracy_details(recs, dets, classes)
+    host_phr = evaluate.phrase_accuracy_details(recs, dets, classes)
+    cnt = counts.cpu().numpy()
+    ok_acc = bool(np.array_equal(cnt[0], host_box["class_match_count"]) and
+                  np.array_equal(cnt[1], host_box["class_count"]) and
+                  np.array_equal(cnt[0], host_phr["class_match_count"]))
+    n_or = min(128, S_r)  # the sequential oracle on a bounded prefix
+    k_or = sum(1 for i in dets[0] if i < n_or * Ns)
+    d_or = [x[:k_or] for x in dets]
+    ok_oracle = bool(np.array_equal(oeval.box_accuracy(recs[:n_or * Ns], d_or, classes)["class_match_count"],
+                                    evaluate.box_accuracy_details(recs[:n_or * Ns], d_or, classes)["class_match_count"]))
+    flags = torch.tensor([int(ok_picks), int(ok_boxes), int(ok_acc), int(ok_oracle)], device=dev)
+    tot = counts.to(torch.int64).clone()
+    if world > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return
+    macro, micro = accuracy_from_counts(tot[0], tot[1])
+    flags = [bool(x) for x in flags.cpu().tolist()]
+    line = dict(metric="video segments/sec (inference sweep: NMS -> RoIAlign -> DVSA eval -> record + accuracy)",
+                value=S / (ms_total / 1e3), unit=UNIT, n_gpus=world, steps=n_steps, warmup=min(Wm, 3) + 1,
+                ms_per_step=ms_total / n_steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f32", data="synthetic", gpu_launches=n_steps * EvalStep.KERNELS_PER_STEP,
+                config={"workload": "cfg5: %d cfg1-shaped segments (5 frames x 2352 proposals -> top-20, 512x38x50 maps, "
+                                    "%d queries of 13 slots, eval phase, batch_size_val 1) sharded %d per rank, %d segments "
+                                    "per launch set" % (S, c["queries"], (S + world - 1) // world, G),
+                        "parallelism": "dp%d (segments sharded, no data-path collective; per-class counters summed once)" % world,
+                        "l2": "two alternating map sets, 156 MB + 80 MB per launch set vs 126 MB L2",
+                        "schedule": "eager launches, 4 kernels per launch set on one stream, no host sync inside the sweep"},
+                parity=dict(picks_bit_exact=flags[0], recorded_boxes_bit_exact=flags[1],
+                            device_accuracy_equals_host_evaluation=flags[2], host_evaluation_equals_oracle=flags[3],
+                            segments_checked_per_rank=nchk, macro_box_accuracy=macro, micro_box_accuracy=micro,
+                            detections=int(tot[1].sum())),
+                clocks=clocks)
+    print(json.dumps(line))
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.cfg == "cfg5":
+        run_sweep(args)
     else:
         run_ours(args)
     try:

@@ -731,7 +731,10 @@ struct BwdParams {
   int train;
 };
 
-constexpr int kBwdThreads = 512;
+#ifndef NAFAE_BWD_THREADS
+#define NAFAE_BWD_THREADS 512
+#endif
+constexpr int kBwdThreads = NAFAE_BWD_THREADS;
 constexpr int kMaxNsLocal = 64;  // frames per segment handled by the fused backward
 
 // d(margin_loss)/dS[a,s,c] for all s of one (segment, column), from shared-memory copies:
@@ -789,7 +792,7 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 // shared memory with one round of independent loads; gather loops issue loads in batches.
 // min 2 CTAs/SM: caps the kernel at 64 registers (66 without the bound = ONE 512-thread CTA per SM by
 // registers, i.e. 16 resident CTAs on the 16 SMs the pipelined step leaves to the head: 15 waves)
-__global__ void __launch_bounds__(kBwdThreads, 2) ground_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kBwdThreads, 1024 / kBwdThreads) ground_bwd_kernel(const BwdParams p) {
   NAFAE_CTA_TRACE(cta_trace, 4);
   extern __shared__ __align__(16) float sm[];
   __shared__ int s_nlive;
@@ -1257,7 +1260,9 @@ NAFAE_API int nafae_ground_backward(const float* grad_margin_loss, const float* 
   p.vis_lam = vis_lam;
   p.train = train ? 1 : 0;
   // shared memory: the largest of the three CTA roles
-  size_t smem = ((size_t)d.Ns * d.NQ + (size_t)d.Ns * d.Na + 3 * (size_t)d.NQ + (size_t)kRowTile * d.D + 4) * 4;
+  // (the accumulator tile holds min(Nb, kRowTile) rows: 40 KB at Nb = 20, so that several CTAs fit an SM)
+  size_t smem = ((size_t)d.Ns * d.NQ + (size_t)d.Ns * d.Na + 3 * (size_t)d.NQ +
+                 (size_t)(d.Nb < kRowTile ? d.Nb : kRowTile) * d.D + 4) * 4;
   const size_t smem_w = (size_t)4 * d.F * 4;
   const size_t smem_c = ((size_t)d.Ns * d.D + (size_t)d.D + 4 * (size_t)d.Ns) * 4;
   if (smem_w > smem) smem = smem_w;

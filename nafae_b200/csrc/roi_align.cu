@@ -556,6 +556,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
         empty_f = f;
         continue;
       }
+      bool first_chunk = true;
       for (;;) {  // one item per table chunk (a single one unless the frame has > kTabCap RoIs)
         wait_released(it - p.stages);
         issue_slab(f, gidx);  // in flight while the table is built
@@ -579,7 +580,9 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
         }
         geometry(h * kTabHalf, n);
         const bool complete = r_next >= p.R;
-        half_f[h] = complete ? f : -1;  // only a complete table can be reused by later units
+        // only a table that holds ALL RoIs of the frame can be reused by later units of that frame
+        half_f[h] = (complete && first_chunk) ? f : -1;
+        first_chunk = false;
         half_n[h] = n;
         half_use[h] = it;
         if (whole) {

@@ -76,7 +76,32 @@ CONFIGS = {
     # configs[3]: dense-proposal stress
     "cfg4": dict(Na=1, Ns=32, Nb=100, Ne=13, D=512, H=38, W=50, C=512, n=300, pre=6000,
                  img_h=608, img_w=800, train=False, Delta=5.0, vis_lam=1.0),
+    # configs[4]: inference sweep -- 10 000 cfg1-shaped segments (eval phase, batch_size_val = 1),
+    # G segments per launch set, sharded contiguously over the ranks
+    "cfg5": dict(Na=1, Ns=5, Nb=20, Ne=13, D=512, H=38, W=50, C=512, n=2352, pre=6000,
+                 img_h=608, img_w=800, train=False, Delta=5.0, vis_lam=1.0, G=8, segments=10000,
+                 queries=4, classes=67, pool=64),
 }
+
+
+def sweep_pool(c, seed=4242):
+    """Host-side pieces of the cfg5 sweep that do not depend on the sharding: a pool of `pool`
+    segments' proposals / scores (segment s uses entry s % pool), the class ids of every segment's
+    queries (without replacement from `classes`, -1 in padded slots) and one ground-truth box per
+    (segment, frame, query): a jittered copy of one of that frame's first 40 proposals."""
+    rs = np.random.RandomState(seed)
+    P, Ns, Ne, S, Q = c["pool"], c["Ns"], c["Ne"], c["segments"], c["queries"]
+    props, scores = proposals(rs, P * Ns, c["n"], c["img_h"], c["img_w"])
+    cls = np.full((S, Ne), -1, np.int32)
+    for s in range(S):
+        cls[s, :Q] = rs.choice(c["classes"], Q, replace=False)
+    pick = rs.randint(0, 40, (S, Ns, Ne))
+    base = props.reshape(P, Ns, c["n"], 4)[np.arange(S)[:, None, None] % P, np.arange(Ns)[None, :, None], pick]
+    gt = base.astype(np.float64) + rs.uniform(-6, 6, (S, Ns, Ne, 4))
+    gt[..., 2:] = np.maximum(gt[..., 2:], gt[..., :2] + 1)
+    lens = np.full((S,), Q, np.int32)
+    return dict(proposals=props.reshape(P, Ns, c["n"], 4), scores=scores.reshape(P, Ns, c["n"]),
+                classes=cls, gt_boxes=gt, lens=lens)
 
 
 def make_batch(cfg, seed):

@@ -251,7 +251,7 @@ def test_reference_named_launchers():
     ("cfg2_like", 40, 64, 38, 50, [20] * 40, False),
     ("real_14x14", 40, 64, 14, 14, [20] * 40, False),
     ("ragged_shuffled_empty_frames", 9, 32, 38, 50, [3, 0, 40, 1, 17, 0, 60, 52, 53], True),
-    ("whole_table_and_chunked", 4, 16, 38, 50, [300, 5, 130, 104], True),
+    ("whole_table_and_chunked", 4, 32, 38, 50, [300, 5, 130, 104], True),
     ("more_than_1024_rois", 12, 8, 38, 50, [100] * 12, False),
 ])
 def test_dynamic_unit_claiming_equals_static_split(name, F, C, H, W, per_frame, shuffle):
@@ -283,9 +283,14 @@ def test_dynamic_unit_claiming_equals_static_split(name, F, C, H, W, per_frame, 
         assert torch.equal(got, static), (name, it)
         assert int(ws[16:16 + F].abs().sum()) == 0 and int(ws[8]) == 0 and int(ws[0]) == 0
     assert int(ws[1]) == 2  # two gated launches opened the gate, the NO_GATE one did not
-    # fewer SMs than units, and a single CTA
-    prev = _C.lib.nafae_set_reserved_sms(140)
+    # fewer CTAs than units (every CTA serves several units of a frame: table reuse), two, one
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    prev = _C.lib.nafae_set_reserved_sms(0)
     try:
-        assert torch.equal(run(ws), static)
+        for ctas in (8, 3, 2, 1):
+            _C.lib.nafae_set_reserved_sms(sms - ctas)
+            for _ in range(2):
+                assert torch.equal(run(ws), static), (name, ctas)
+            assert torch.equal(run(None), static), (name, ctas, "static")
     finally:
         _C.lib.nafae_set_reserved_sms(prev)

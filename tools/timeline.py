@@ -106,6 +106,8 @@ for i in range(len(r)):
     tmax = max(tmax, int(r["t1"][i]))
 segs.append((start, len(r)))
 print("segments (replays):", len(segs), [b - a for a, b in segs])
+gaps = [(int(r["t0"][segs[i + 1][0]]) - int(r["t1"][segs[i][0]:segs[i][1]].max())) / 1e3 for i in range(len(segs) - 1)]
+print("idle gap between consecutive replays (last CTA end -> first CTA start), us:", ["%.1f" % g for g in gaps])
 for (sa, sb) in segs[-2:]:
     seg = r[sa:sb]
     base = int(seg["t0"].min())
