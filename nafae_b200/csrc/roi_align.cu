@@ -233,14 +233,15 @@ align_bwd_generic(const float* __restrict__ top_diff, const float* __restrict__ 
 // a ring of `stages` buffers with full/empty mbarriers.
 //
 // PRODUCER WARP (all 32 lanes) -- scheduling, loads and RoI tables:
-//   * units are CLAIMED dynamically, with frame affinity: one claim counter per frame in the
-//     workspace; CTA b starts at frame b*B/grid (so ~grid/B CTAs share a frame, as a static split
-//     would) and moves on to the nearest frame with unclaimed units when its own runs dry.  A CTA
-//     that starts late (a concurrent kernel still holds its SM) or draws expensive frames simply
-//     claims fewer units: the kernel ends when the work ends, not when the unluckiest static share
-//     ends (round 1: avg 73.0 k vs max 84.5 k active cycles per SM).  Near the end of its expected
-//     share a CTA claims only one unit ahead of the one being processed (instead of stages-1), so
-//     the tail is at most about one unit.  Without a workspace the split is static and contiguous.
+//   * units are split into contiguous ranges, one per CTA (a range touches 1-2 frames, so RoI
+//     tables are rebuilt once or twice per CTA).  A CTA works through the PREFIX of its range without
+//     any coordination; the last kTail units of every range are a TAIL that is claimed through a
+//     counter in the workspace: the owner claims its own tail first (the atomic is issued one item
+//     ahead, its latency never delays a bulk copy), and a CTA that runs out of work early STEALS
+//     tail units from the nearest range that still has some.  A CTA that starts late (a concurrent
+//     kernel still holds its SM) or drew expensive frames sheds up to kTail units instead of
+//     setting the kernel's end time (round 1: avg 73.0 k vs max 84.5 k active cycles per SM).
+//     Without a workspace the split is purely static.
 //   * the RoI table of a frame (cells + weights of its 8x8 sample grid per RoI) is built by the
 //     producer warp into one of two half buffers while the slab is in flight; consumer warps never
 //     build tables and never meet at a CTA-wide barrier.  Frames with more than half / all of the
@@ -274,9 +275,14 @@ constexpr int kFrRegs = 32;         // frame ids cached per producer lane (R <= 
 #ifndef NAFAE_SLAB_SCAV_DEPTH
 #define NAFAE_SLAB_SCAV_DEPTH 2
 #endif
-constexpr int kScavDepth = NAFAE_SLAB_SCAV_DEPTH;  // items in the ring while scavenging other frames
+constexpr int kScavDepth = NAFAE_SLAB_SCAV_DEPTH;  // items in the ring while stealing from other ranges
+#ifndef NAFAE_SLAB_TAIL
+#define NAFAE_SLAB_TAIL 3
+#endif
+constexpr int kTail = NAFAE_SLAB_TAIL;             // stealable units at the end of every CTA's range
 // workspace words (ints): [0] residency arrivals, [1] gate epoch, [2..7] epochs seen per waiting slot,
-// [8] exit ticket, [16 + f] claim counter of frame f
+// [8] exit ticket, [16 + b] tail units claimed from the range of CTA b
+constexpr int kMaxSlabCtas = 1024;  // tail counters in the workspace (persistent grid <= SM count)
 constexpr int kWsExit = 8;
 constexpr int kWsSched = 16;
 
@@ -368,10 +374,20 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
       fr[i] = (fr_cached && r < p.R) ? (int)__ldg(p.rois + (size_t)r * 5) : -1;
     }
     const uint32_t chan_bytes = (uint32_t)p.hw * 4u;
-    const bool dynamic = p.sched != nullptr;
-    int cur_f = (int)((long long)p.B * blockIdx.x / gridDim.x);       // dynamic: frame being drained
-    int u_next = (int)((long long)p.units * blockIdx.x / gridDim.x);  // static: contiguous range
-    const int u_end = (int)((long long)p.units * (blockIdx.x + 1) / gridDim.x);
+    const bool dynamic = p.sched != nullptr && kTail > 0;
+    // contiguous range of this CTA; with a workspace its last kTail units are claimed, not owned
+    auto range_begin = [&](int b) { return (int)((long long)p.units * b / gridDim.x); };
+    auto tail_of = [&](int b, int* first) {  // number of tail units of range b, *first = the first one
+      const int lo = range_begin(b), hi = range_begin(b + 1);
+      const int t = hi - lo < kTail ? hi - lo : kTail;
+      *first = hi - t;
+      return t;
+    };
+    int u_next = range_begin(blockIdx.x);
+    const int u_end = range_begin(blockIdx.x + 1);
+    int tail_first = u_end;
+    const int my_tail = dynamic ? tail_of(blockIdx.x, &tail_first) : 0;
+    const int prefix_end = u_end - my_tail;
     int it = 0;                     // items published so far
     int half_f[2] = {-1, -1};       // frame whose complete table sits in half h (-2: part of a whole-buffer table)
     int half_n[2] = {0, 0};
@@ -462,52 +478,53 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
       }
       __syncwarp();
     };
-    // Dynamic claiming.  OWN mode: the CTA drains the frame it was dealt (cur_f) -- the atomic for
-    // the NEXT unit is issued right after an item is published and its result is only read after the
-    // wait for a free stage, so its L2 round trip never delays a bulk copy.  When the frame runs
-    // dry the CTA SCAVENGES the nearest frame that still has unclaimed units, one synchronous claim
-    // at a time and only one unit ahead of the one being processed, so that no CTA sits on claimed
-    // work while others are idle at the tail; a frame with plenty left is adopted (back to OWN).
-    int pend = 0;            // lane 0: result of the claim in flight (OWN mode)
-    bool scavenging = false;
+    // Tail claiming.  The owner's claim on its own tail is issued one item ahead (start_claim) and
+    // only read after the wait for a free stage.  Stealing is synchronous and keeps only one unit
+    // ahead of the one being processed, so that nobody sits on stolen work while others are idle.
+    int pend = 0;           // lane 0: result of the own-tail claim in flight
+    bool own_tail = true;   // still claiming from the own range's tail
+    bool stealing = false;
+    int victim = (int)blockIdx.x;
     auto start_claim = [&]() {
-      if (lane == 0) pend = atomicAdd(p.sched + cur_f, 1);
+      if (lane == 0) pend = atomicAdd(p.sched + blockIdx.x, 1);
     };
-    auto scavenge = [&]() -> int {  // -1: no work left anywhere
-      while (cur_f >= 0) {
+    auto steal = [&]() -> int {  // -1: no tail unit left anywhere
+      while (victim >= 0) {
         int found = -1;
-        for (int base = 0; base < p.B && found < 0; base += 32) {
-          const int k = base + lane;  // distance from cur_f (0: cur_f itself)
-          int f = cur_f + k;
-          if (f >= p.B) f -= p.B;
-          const bool open = k < p.B && __ldcg(p.sched + f) < p.groups;
+        for (int base = 1; base < (int)gridDim.x && found < 0; base += 32) {
+          const int k = base + lane;  // distance from the last victim
+          int b = victim + k;
+          if (b >= (int)gridDim.x) b -= gridDim.x;
+          int first;
+          const bool open = k < (int)gridDim.x && __ldcg(p.sched + b) < tail_of(b, &first);
           const unsigned bal = __ballot_sync(0xffffffffu, open);
           if (bal) {
-            found = cur_f + base + __ffs(bal) - 1;
-            if (found >= p.B) found -= p.B;
+            found = victim + base + __ffs(bal) - 1;
+            if (found >= (int)gridDim.x) found -= gridDim.x;
           }
         }
-        cur_f = found;
+        victim = found;
         if (found < 0) break;
         int g = 0;
         if (lane == 0) g = atomicAdd(p.sched + found, 1);
         g = __shfl_sync(0xffffffffu, g, 0);
-        if (g < p.groups) {
-          if (g + 8 < p.groups) scavenging = false;  // plenty left: adopt this frame
-          return found * p.groups + g;
-        }
+        int first;
+        if (g < tail_of(found, &first)) return first + g;
+        victim = found;  // raced: look further from here
       }
       return -1;
     };
     // next unit of this CTA, -1 when there is none (warp-uniform)
     auto claim = [&]() -> int {
-      if (!dynamic) return u_next < u_end ? u_next++ : -1;
-      if (!scavenging) {
+      if (u_next < prefix_end) return u_next++;
+      if (!dynamic) return -1;
+      if (own_tail) {
         const int g = __shfl_sync(0xffffffffu, pend, 0);
-        if (g < p.groups) return cur_f * p.groups + g;
-        scavenging = true;
+        if (g < my_tail) return tail_first + g;
+        own_tail = false;
+        stealing = true;
       }
-      return scavenge();
+      return steal();
     };
     // publish one item: slab of unit (f, gidx) + table range [j0, j0+n)
     auto issue_slab = [&](int f, int gidx) {
@@ -530,15 +547,16 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
       ++it;
     };
 
-    if (dynamic) start_claim();  // in flight while the frame ids load
+    if (dynamic && u_next >= prefix_end) start_claim();  // a range without a prefix starts on its tail
     for (;;) {
-      // room for one more item?  `stages` deep while draining the own frame, one unit ahead of the
-      // one being processed while scavenging
-      const int depth = (!dynamic || !scavenging) ? p.stages : (p.stages < kScavDepth ? p.stages : kScavDepth);
+      // room for one more item?  `stages` deep on the own range, one unit ahead of the one being
+      // processed while stealing
+      const int depth = !stealing ? p.stages : (p.stages < kScavDepth ? p.stages : kScavDepth);
       wait_released(it - depth);
       const int u = claim();
       if (u < 0) break;
-      if (dynamic && !scavenging) start_claim();  // the next one: hidden behind this item's work
+      // the next unit comes from the own tail: get its claim going now, hidden behind this item
+      if (dynamic && own_tail && u_next >= prefix_end) start_claim();
       const int f = u / p.groups, gidx = u - f * p.groups;
       if (f == empty_f) continue;
       int h = half_f[0] == f ? 0 : (half_f[1] == f ? 1 : -1);
@@ -610,7 +628,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
       __threadfence();
       int* exit_ticket = p.sched - kWsSched + kWsExit;
       if (atomicAdd(exit_ticket, 1) == (int)gridDim.x - 1) {
-        for (int f = 0; f < p.B; ++f) p.sched[f] = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) p.sched[b] = 0;
         *exit_ticket = 0;
       }
     }
@@ -769,7 +787,8 @@ int launch_slab(const SlabParams& p, int pool, size_t smem, cudaStream_t stream)
     set_error("roi_align: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     return -(int)e;
   }
-  const int grid = slab_grid(p.units, p.sched != nullptr);
+  int grid = slab_grid(p.units, p.sched != nullptr);
+  if (grid > kMaxSlabCtas) grid = kMaxSlabCtas;
   kern<<<grid, kSlabThreads, smem, stream>>>(p);
   return launch_status("align_pool_fwd_slab");
 }
@@ -849,9 +868,10 @@ NAFAE_CTA_TRACE_READER(nafae_debug_cta_trace_roi_align)
 NAFAE_API int nafae_roi_align_persistent_ctas(int num_units) { return slab_grid(num_units, true); }
 
 NAFAE_API size_t nafae_roi_align_workspace_bytes(int batch_size, int num_rois) {
+  (void)batch_size;
   (void)num_rois;
-  // the residency gate + one claim counter per frame (the RoI tables live in shared memory)
-  return align_up((size_t)NAFAE_ROI_ALIGN_WS_BYTES + sizeof(int) * (size_t)(batch_size > 0 ? batch_size : 0), 64);
+  // the residency gate + one tail counter per persistent CTA (the RoI tables live in shared memory)
+  return (size_t)NAFAE_ROI_ALIGN_WS_BYTES + sizeof(int) * kMaxSlabCtas;
 }
 
 NAFAE_API int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size,
