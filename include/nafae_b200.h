@@ -245,6 +245,22 @@ int nafae_eval_record(const int64_t* D_ind, const float* D_sim, const int* entit
                       const double* gt_boxes, const int* gt_classes, float gt_thr, int num_classes,
                       int* class_match, int* class_count, cudaStream_t stream);
 
+/* ------------------------------------------------------- bridge: tensor-core GEMM ---- */
+
+/* First slice of the "bridge" between RoIAlign and the scoring head: the frozen, inference-only fully
+ * connected layers of RCNN_top -- lib/model/faster_rcnn/vgg16_rpn.py:35,56-61 (VGG16 fc6 / fc7:
+ * Linear + ReLU; the Dropout between them is a no-op because the detector runs in eval mode,
+ * model.py:651,673) -- as one tcgen05 (5th-generation tensor core) kernel per layer:
+ *     C[M, N] = act(A[M, K] . B[N, K]^T + bias[N])
+ * A (M, K) bf16 row-major = the pooled RoI features viewed as (R, C*7*7) (vgg16_rpn.py:58); B (N, K)
+ * bf16 row-major = nn.Linear.weight as PyTorch stores it; bias (N) fp32 or NULL; C (M, N) fp32, or bf16
+ * with NAFAE_GEMM_OUT_BF16 (feeds the next layer).  fp32 accumulation in tensor memory.  K % 8 == 0,
+ * 16-byte aligned buffers.  bf16 inputs: expect ~1e-2 relative agreement with the fp32 layer. */
+#define NAFAE_GEMM_RELU 1u
+#define NAFAE_GEMM_OUT_BF16 2u
+int nafae_gemm_bf16_tn(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
+                       unsigned flags, cudaStream_t stream);
+
 /* ------------------------------------------------------- step wrapper: clip + Adam ---- */
 
 /* Replaces clip_grad_norm_(ground_model.parameters(), args.clip) + optimizer.step() --

@@ -66,6 +66,7 @@ SIGNATURES = {
     "nafae_eval_record": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "nafae_gemm_bf16_tn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_uint, c_void_p]),
     "nafae_clip_adam_workspace_bytes": (c_size_t, []),
     "nafae_clip_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float,
                                      c_float, c_float, c_float, c_float, c_void_p, c_size_t, c_void_p]),

@@ -9,6 +9,41 @@ import torch
 from torch import nn
 
 
+class RCNNTop(nn.Module):
+    """Inference-only `RCNN_top` of the frozen detector (lib/model/faster_rcnn/vgg16_rpn.py:35,56-61:
+    VGG16 fc6 + ReLU + Dropout, fc7 + ReLU + Dropout in eval mode) on the tcgen05 tensor cores:
+    weights are converted to bf16 once, each layer is one `nafae_gemm_bf16_tn` launch (bias + ReLU in
+    the epilogue), accumulation is fp32.  `forward(pooled)` takes the RoIAlign output viewed as
+    (R, C*7*7) in fp32 (cast here) or bf16 and returns fc7 features (R, out) in fp32 -- the input of
+    `VisEbd`.  The detector is frozen in NAFAE (model.py:651,673), so there is no backward."""
+
+    def __init__(self, fc6, fc7):
+        super(RCNNTop, self).__init__()
+        self.w6 = nn.Parameter(fc6.weight.detach().to(torch.bfloat16).contiguous(), requires_grad=False)
+        self.b6 = nn.Parameter(fc6.bias.detach().float().contiguous(), requires_grad=False)
+        self.w7 = nn.Parameter(fc7.weight.detach().to(torch.bfloat16).contiguous(), requires_grad=False)
+        self.b7 = nn.Parameter(fc7.bias.detach().float().contiguous(), requires_grad=False)
+
+    @torch.no_grad()
+    def forward(self, pooled):
+        from . import _C
+        _C.require_cuda(pooled, "pooled")
+        x = pooled.reshape(pooled.shape[0], -1)
+        if x.dtype != torch.bfloat16:
+            x = x.to(torch.bfloat16)
+        x = x.contiguous()
+        R = x.shape[0]
+        h = torch.empty((R, self.w6.shape[0]), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((R, self.w7.shape[0]), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            s = _C.stream(x.device)
+            _C.check(_C.lib.nafae_gemm_bf16_tn(_C.ptr(x), _C.ptr(self.w6), _C.ptr(self.b6), _C.ptr(h), R,
+                                               self.w6.shape[0], self.w6.shape[1], 3, s), "nafae_gemm_bf16_tn(fc6)")
+            _C.check(_C.lib.nafae_gemm_bf16_tn(_C.ptr(h), _C.ptr(self.w7), _C.ptr(self.b7), _C.ptr(y), R,
+                                               self.w7.shape[0], self.w7.shape[1], 1, s), "nafae_gemm_bf16_tn(fc7)")
+        return y
+
+
 class VisEbd(nn.Module):
     """model.py:616-629: RoI fc7 features (R, vis_fc_dim) -> tanh(drop(fc1(x / 100)))."""
 

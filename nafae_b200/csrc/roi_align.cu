@@ -271,7 +271,6 @@ constexpr int kSlabThreads = kConsThreads + 32;  // + producer warp
 constexpr int kTabCap = 104;        // RoI table entries in shared memory
 constexpr int kTabHalf = kTabCap / 2;
 constexpr int kStagesMax = 4;
-constexpr int kFrRegs = 32;         // frame ids cached per producer lane (R <= 1024)
 #ifndef NAFAE_SLAB_SCAV_DEPTH
 #define NAFAE_SLAB_SCAV_DEPTH 2
 #endif
@@ -366,13 +365,6 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
 
   if (warp == kConsWarps) {
     // ============================================================ producer warp ====
-    const bool fr_cached = p.R <= kFrRegs * 32;
-    int fr[kFrRegs];  // frame id of RoI lane + 32*i (one L2 round trip, then register scans)
-#pragma unroll
-    for (int i = 0; i < kFrRegs; ++i) {
-      const int r = lane + 32 * i;
-      fr[i] = (fr_cached && r < p.R) ? (int)__ldg(p.rois + (size_t)r * 5) : -1;
-    }
     const uint32_t chan_bytes = (uint32_t)p.hw * 4u;
     const bool dynamic = p.sched != nullptr && kTail > 0;
     // contiguous range of this CTA; with a workspace its last kTail units are claimed, not owned
@@ -392,7 +384,6 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
     int half_f[2] = {-1, -1};       // frame whose complete table sits in half h (-2: part of a whole-buffer table)
     int half_n[2] = {0, 0};
     int half_use[2] = {-1, -1};     // last item that reads half h
-    int empty_f = -1;               // a frame known to have no RoIs
 
     // all consumer warps are done with `item`.  Items older than it - stages have been waited for
     // already (their stage has been re-armed since: the parity test would alias), so only the
@@ -402,48 +393,40 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
         mbar_wait(&empty[item % p.stages], (uint32_t)(item / p.stages) & 1u);
     };
     // RoIs r >= r0 of frame f, ascending, at most kTabCap of them -> scan_list; returns the count,
-    // *next = where the following chunk starts (>= R: none left)
+    // *next = where the following chunk starts (>= R: none left).  Frame ids come from global memory
+    // (L1 / L2 hits after the first scan), eight 32-RoI loads in flight.
     auto scan = [&](int f, int r0, int* next) -> int {
       int n = 0;
       *next = p.R;
-      auto step = [&](int base, int frv) -> bool {  // true: list full
-        const int r = base + lane;
-        const bool hit = r < p.R && r >= r0 && frv == f;
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        const int cnt = __popc(bal);
-        const int pos = n + __popc(bal & ((1u << lane) - 1u));
-        if (hit && pos < kTabCap) scan_list[pos] = r;
-        if (n + cnt > kTabCap) {
-          *next = base + (int)__fns(bal, 0, kTabCap - n + 1);  // first hit that did not fit
-          n = kTabCap;
-          return true;
-        }
-        n += cnt;
-        if (n == kTabCap) {
-          *next = base + 32;
-          return true;
-        }
-        return false;
-      };
-      if (fr_cached) {
+      bool done = false;
+      for (int base0 = r0 / 32 * 32; base0 < p.R && !done; base0 += 256) {
+        int v[8];
 #pragma unroll
-        for (int i = 0; i < kFrRegs; ++i) {
-          if (32 * i >= p.R) break;
-          if (32 * i + 32 <= r0) continue;
-          if (step(32 * i, fr[i])) break;
+        for (int j = 0; j < 8; ++j) {
+          const int r = base0 + 32 * j + lane;
+          v[j] = r < p.R ? (int)__ldg(p.rois + (size_t)r * 5) : -1;
         }
-      } else {
-        bool done = false;
-        for (int base0 = r0 / 32 * 32; base0 < p.R && !done; base0 += 256) {
-          int v[8];  // eight independent loads in flight
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int r = base0 + 32 * j + lane;
-            v[j] = r < p.R ? (int)__ldg(p.rois + (size_t)r * 5) : -1;
+        for (int j = 0; j < 8; ++j) {
+          const int base = base0 + 32 * j;
+          if (done || base >= p.R) continue;
+          const int r = base + lane;
+          const bool hit = r < p.R && r >= r0 && v[j] == f;
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          const int cnt = __popc(bal);
+          const int pos = n + __popc(bal & ((1u << lane) - 1u));
+          if (hit && pos < kTabCap) scan_list[pos] = r;
+          if (n + cnt > kTabCap) {
+            *next = base + (int)__fns(bal, 0, kTabCap - n + 1);  // first hit that did not fit
+            n = kTabCap;
+            done = true;
+          } else {
+            n += cnt;
+            if (n == kTabCap) {
+              *next = base + 32;
+              done = true;
+            }
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (!done && base0 + 32 * j < p.R) done = step(base0 + 32 * j, v[j]);
         }
       }
       __syncwarp();
@@ -479,8 +462,8 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
       __syncwarp();
     };
     // Tail claiming.  The owner's claim on its own tail is issued one item ahead (start_claim) and
-    // only read after the wait for a free stage.  Stealing is synchronous and keeps only one unit
-    // ahead of the one being processed, so that nobody sits on stolen work while others are idle.
+    // only read when the unit is needed.  Stealing is synchronous and keeps only one unit ahead of the
+    // one being processed, so that nobody sits on stolen work while others are idle.
     int pend = 0;           // lane 0: result of the own-tail claim in flight
     bool own_tail = true;   // still claiming from the own range's tail
     bool stealing = false;
@@ -510,7 +493,6 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
         g = __shfl_sync(0xffffffffu, g, 0);
         int first;
         if (g < tail_of(found, &first)) return first + g;
-        victim = found;  // raced: look further from here
       }
       return -1;
     };
@@ -526,92 +508,65 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
       }
       return steal();
     };
-    // publish one item: slab of unit (f, gidx) + table range [j0, j0+n)
-    auto issue_slab = [&](int f, int gidx) {
-      const int stage = it % p.stages;
-      if (lane == 0) {
-        const float* src = p.bottom + ((size_t)f * p.C + (size_t)gidx * p.cg) * p.hw;
-        float* dst = slabs + stage_floats * stage;
-        mbar_arrive_expect_tx(&full[stage], chan_bytes * p.cg);
-        for (int c = 0; c < p.cg; ++c)
-          bulk_g2s(dst + (size_t)c * hwp, src + (size_t)c * p.hw, chan_bytes, &full[stage]);
-      }
-    };
-    auto publish = [&](int f, int gidx, int j0, int n) {
-      const int stage = it % p.stages;
-      __syncwarp();  // table / roi_id stores of all lanes are ordered before lane 0's release-arrive
-      if (lane == 0) {
-        s_desc[stage] = make_int4(f, gidx, j0, n);
-        mbar_arrive(&full[stage]);
-      }
-      ++it;
-    };
 
     if (dynamic && u_next >= prefix_end) start_claim();  // a range without a prefix starts on its tail
     for (;;) {
-      // room for one more item?  `stages` deep on the own range, one unit ahead of the one being
-      // processed while stealing
-      const int depth = !stealing ? p.stages : (p.stages < kScavDepth ? p.stages : kScavDepth);
-      wait_released(it - depth);
-      const int u = claim();
+      const int u = claim();  // known before the ring has room: the copy below leaves at once
       if (u < 0) break;
       // the next unit comes from the own tail: get its claim going now, hidden behind this item
       if (dynamic && own_tail && u_next >= prefix_end) start_claim();
       const int f = u / p.groups, gidx = u - f * p.groups;
-      if (f == empty_f) continue;
-      int h = half_f[0] == f ? 0 : (half_f[1] == f ? 1 : -1);
-      if (h >= 0) {  // table already on chip
-        wait_released(it - p.stages);
-        issue_slab(f, gidx);
-        half_use[h] = it;
-        if (half_f[1] == -2) half_use[1] = it;  // whole-buffer table
-        publish(f, gidx, h * kTabHalf, half_n[h]);
-        continue;
-      }
-      int r_next = 0;
-      int n = scan(f, 0, &r_next);
-      if (n == 0) {
-        empty_f = f;
-        continue;
-      }
+      int r_next = 0, n = 0;
       bool first_chunk = true;
-      for (;;) {  // one item per table chunk (a single one unless the frame has > kTabCap RoIs)
-        wait_released(it - p.stages);
-        issue_slab(f, gidx);  // in flight while the table is built
-        const bool whole = n > kTabHalf;
-        if (whole) {
-          wait_released(half_use[0]);
-          wait_released(half_use[1]);
-          h = 0;
+      do {  // one item per table chunk (a single one unless the frame has > kTabCap RoIs)
+        // room for one more item?  `stages` deep on the own range, one unit ahead of the one being
+        // processed while stealing
+        const int depth = !stealing ? p.stages : (p.stages < kScavDepth ? p.stages : kScavDepth);
+        wait_released(it - depth);
+        const int stage = it % p.stages;
+        if (lane == 0) {  // the slab is in flight while the table is looked up / built
+          const float* src = p.bottom + ((size_t)f * p.C + (size_t)gidx * p.cg) * p.hw;
+          float* dst = slabs + stage_floats * stage;
+          mbar_arrive_expect_tx(&full[stage], chan_bytes * p.cg);
+          for (int c = 0; c < p.cg; ++c)
+            bulk_g2s(dst + (size_t)c * hwp, src + (size_t)c * p.hw, chan_bytes, &full[stage]);
+        }
+        int h = first_chunk ? (half_f[0] == f ? 0 : (half_f[1] == f ? 1 : -1)) : -1;
+        if (h >= 0) {  // table already on chip
+          n = half_n[h];
+          r_next = p.R;
+          half_use[h] = it;
+          if (half_f[1] == -2) half_use[1] = it;  // whole-buffer table
         } else {
-          // the half that is not serving the most recent item
-          h = half_use[0] <= half_use[1] ? 0 : 1;
-          if (half_f[1] == -2) {  // a whole-buffer table is being replaced: both halves must drain
+          n = scan(f, r_next, &r_next);
+          const bool whole = n > kTabHalf;
+          if (whole || half_f[1] == -2) {  // both halves are involved: both must drain
             wait_released(half_use[0]);
             wait_released(half_use[1]);
-            half_f[1] = -1;
-            half_f[0] = -1;
+            half_f[0] = half_f[1] = -1;
             h = 0;
-          } else {
+          } else {  // the half that is not serving the most recent item
+            h = half_use[0] <= half_use[1] ? 0 : 1;
             wait_released(half_use[h]);
           }
+          geometry(h * kTabHalf, n);
+          // only a table that holds ALL RoIs of the frame can be reused by later units of that frame
+          half_f[h] = (r_next >= p.R && first_chunk) ? f : -1;
+          half_n[h] = n;
+          half_use[h] = it;
+          if (whole) {
+            half_f[1] = -2;
+            half_use[1] = it;
+          }
         }
-        geometry(h * kTabHalf, n);
-        const bool complete = r_next >= p.R;
-        // only a table that holds ALL RoIs of the frame can be reused by later units of that frame
-        half_f[h] = (complete && first_chunk) ? f : -1;
         first_chunk = false;
-        half_n[h] = n;
-        half_use[h] = it;
-        if (whole) {
-          half_f[1] = -2;
-          half_use[1] = it;
+        __syncwarp();  // table / roi_id stores of all lanes are ordered before lane 0's release-arrive
+        if (lane == 0) {
+          s_desc[stage] = make_int4(f, gidx, h * kTabHalf, n);  // n may be 0: an empty item
+          mbar_arrive(&full[stage]);
         }
-        publish(f, gidx, h * kTabHalf, n);
-        if (complete) break;
-        n = scan(f, r_next, &r_next);
-        if (n == 0) break;
-      }
+        ++it;
+      } while (r_next < p.R);
     }
     // no more work: tell the consumers
     wait_released(it - p.stages);
