@@ -59,8 +59,6 @@ def parse_args():
     ap.add_argument("--allreduce", default="auto", choices=["auto", "multicast", "peer"],
                     help="gradient all-reduce kernel: NVLS multimem (in-switch reduction) when the box supports "
                          "NVSwitch multicast, else the bulk-copy peer-memory kernel")
-    ap.add_argument("--static-slab", action="store_true",
-                    help="RoIAlign kernel with the static contiguous unit split (no claim counters)")
     ap.add_argument("--comm-sms", type=int, default=-1, help="SMs kept free for the all-reduce CTAs")
     ap.add_argument("--ar-ctas", type=int, default=-1, help="CTAs of the all-reduce kernel")
     return ap.parse_args()
@@ -238,9 +236,6 @@ def run_ours(args):
 
     host = [synth.make_batch(args.cfg, 1234 + 10 * rank + i) for i in range(2)]
     steps = [make_step() for _ in range(2)]
-    if args.static_slab:
-        for st in steps:
-            st.align_ws_bytes = 64  # gate words only: no claim counters -> static split
     # DP: the gradient all-reduce runs over a flat bucket sized like the reference's trainable
     # parameters; this path's dL/dword_feats is written straight into it
     buckets = None

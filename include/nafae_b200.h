@@ -39,8 +39,8 @@ typedef struct CUstream_st* cudaStream_t; /* same opaque handle as CUDA driver_t
 #define NAFAE_POOL_MAX 2  /* RoIAlignMax : sample (h+1)x(w+1), max_pool2d(kernel 2, stride 1)  */
 
 /* flags */
-#define NAFAE_FLAG_NO_GATE 2u /* nafae_roi_align_forward: use the workspace (dynamic unit scheduling)
-                                 but do not open the residency gate -- nobody waits on this launch */
+#define NAFAE_FLAG_NO_GATE 2u /* nafae_roi_align_forward: ignore the workspace's residency gate --
+                                 nobody waits on this launch (keeps gate epochs paired with waiters) */
 #define NAFAE_FLAG_EXACT 1u /* reference-order arithmetic (mixed fp32/fp64 exactly as the
                                reference kernel evaluates it): bit-identical pooled features,
                                slower.  Default (0) = fp32 FMA path, <= 1e-4 relative. */
@@ -136,16 +136,13 @@ int ROIAlignBackwardLaucher(const float* top_diff, const float spatial_scale, co
  * (R, C, h+1, w+1) intermediate.  out_height x out_width is the MODULE's aligned size (7x7 for
  * RoIAlignAvg(7, 7, 1/16)); with pool_mode != NONE the sampled grid is (out+1) x (out+1).
  * top_data (R, C, out_height, out_width) is fully written (no zero-fill needed).
- * workspace: optional (NULL / 0 is fine).  nafae_roi_align_workspace_bytes(batch_size, num_rois) bytes
- * of device memory, ZERO-INITIALISED ONCE by the caller and then left to the library, private to one
- * stream: the residency gate of nafae_gate_wait (its first NAFAE_ROI_ALIGN_WS_BYTES; a workspace of
- * only that size is accepted and gives the gate alone) followed by one claim counter per frame --
- * with them the persistent kernel's CTAs CLAIM (frame, channel-group) units dynamically instead of
- * splitting them statically, so a CTA that starts late behind a concurrent kernel takes less work. */
+ * workspace: optional (NULL / 0 is fine).  nafae_roi_align_workspace_bytes(batch_size, num_rois)
+ * (= NAFAE_ROI_ALIGN_WS_BYTES) bytes of device memory, ZERO-INITIALISED ONCE by the caller and then
+ * left to the library, private to one stream: the residency gate of nafae_gate_wait. */
 size_t nafae_roi_align_workspace_bytes(int batch_size, int num_rois);
 /* CTAs the persistent RoIAlign kernel launches for `num_units` (frame, 8-channel-group) work units
- * under the current nafae_set_reserved_sms setting when it has a full workspace (dynamic claiming):
- * min(SMs - reserved, num_units) (reporting / capacity planning; no launch). */
+ * under the current nafae_set_reserved_sms setting: the smallest grid whose busiest CTA has no more
+ * units than with every available SM (reporting / capacity planning; no launch). */
 int nafae_roi_align_persistent_ctas(int num_units);
 int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size,
                             int num_rois, int height, int width, int channels, int out_height,

@@ -254,10 +254,10 @@ def test_reference_named_launchers():
     ("whole_table_and_chunked", 4, 32, 38, 50, [300, 5, 130, 104], True),
     ("more_than_1024_rois", 12, 8, 38, 50, [100] * 12, False),
 ])
-def test_dynamic_unit_claiming_equals_static_split(name, F, C, H, W, per_frame, shuffle):
-    """With a full workspace the persistent CTAs claim (frame, channel-group) units dynamically;
-    the arithmetic per unit is the same, so the output must be BIT-identical to the static split
-    (no workspace), launch after launch, and the claim counters must be left zeroed."""
+def test_persistent_grid_size_and_gate_workspace_do_not_change_results(name, F, C, H, W, per_frame, shuffle):
+    """The persistent kernel splits (frame, channel-group) units over however many SMs it is given:
+    148, a handful, or one CTA must produce BIT-identical pooled features, with or without the
+    residency-gate workspace, launch after launch; the gate counts exactly the gated launches."""
     from nafae_b200 import _C
     rs = np.random.RandomState(len(name) * 7 + F)
     feat = _t(synth.conv5_maps(rs, F, C, H, W) - 0.3)
@@ -272,25 +272,23 @@ def test_dynamic_unit_claiming_equals_static_split(name, F, C, H, W, per_frame, 
                                             ws.numel() * 4 if ws is not None else 0, _C.stream())
         assert st == 1, _C.last_error()
         return out
-    static = run(None)
-    _close(static.cpu().numpy(), ocpu.roi_align_avg_forward(feat.cpu().numpy(), rois_np, 7, 7, 1 / 16.))
+    base = run(None)
+    _close(base.cpu().numpy(), ocpu.roi_align_avg_forward(feat.cpu().numpy(), rois_np, 7, 7, 1 / 16.))
     nbytes = int(_C.lib.nafae_roi_align_workspace_bytes(F, R))
-    assert nbytes >= 64 + 4 * F
+    assert nbytes >= _C.ROI_ALIGN_WS_BYTES
     ws = torch.zeros(nbytes // 4, dtype=torch.int32, device=_dev())
     for it in range(3):
         got = run(ws, _C.FLAG_NO_GATE if it == 1 else 0)
         torch.cuda.synchronize()
-        assert torch.equal(got, static), (name, it)
-        assert int(ws[16:16 + F].abs().sum()) == 0 and int(ws[8]) == 0 and int(ws[0]) == 0
+        assert torch.equal(got, base), (name, it)
+        assert int(ws[0]) == 0
     assert int(ws[1]) == 2  # two gated launches opened the gate, the NO_GATE one did not
-    # fewer CTAs than units (every CTA serves several units of a frame: table reuse), two, one
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     prev = _C.lib.nafae_set_reserved_sms(0)
     try:
         for ctas in (8, 3, 2, 1):
             _C.lib.nafae_set_reserved_sms(sms - ctas)
-            for _ in range(2):
-                assert torch.equal(run(ws), static), (name, ctas)
-            assert torch.equal(run(None), static), (name, ctas, "static")
+            assert torch.equal(run(ws), base), (name, ctas)
+            assert torch.equal(run(None), base), (name, ctas, "no workspace")
     finally:
         _C.lib.nafae_set_reserved_sms(prev)
