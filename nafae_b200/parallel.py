@@ -135,11 +135,15 @@ class PeerAllReduce(object):
     kind = "peer"
 
     def __init__(self, numel, device, rank=None, world=None, num_ctas=None, cta_threads=None,
-                 variant=0, width=0):
+                 variant=None, width=0):
         import ctypes
         from . import _C
         self._C, self._ct = _C, ctypes
         # include/nafae_b200.h: NAFAE_AR_VARIANT(v) | NAFAE_AR_WIDTH(w)
+        # variant 1 (3-slot ring, larger chunks, one issuing lane per peer) measured faster than variant
+        # 0 at every width (world 2: 34.9 vs 38.7 us; <W=8>: 52.5 vs 90.1 us for the 8.8 MB bucket)
+        if variant is None:
+            variant = int(os.environ.get("NAFAE_AR_VARIANT", "1"))
         self.flags = (int(variant) & 0xf) | ((int(width) & 0xff) << 8)
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
