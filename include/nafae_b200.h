@@ -211,6 +211,17 @@ int nafae_ground_forward_batched(const float* vis_feats, const float* word_feats
                                  int D, float Delta, float vis_lam, int train, int64_t* D_ind,
                                  float* D_sim, float* margin_loss, void* workspace,
                                  size_t workspace_bytes, cudaStream_t stream);
+/* Same contract and results as nafae_ground_forward, with the regions x queries x dim contraction
+ * (S_ = vis_feats @ word_feats^T, model.py:548) on the tcgen05 tensor cores: 128-row tiles, fp32
+ * operands fed as three tf32 products per K step (hi*hi + lo*hi + hi*lo), fp32 accumulation in tensor
+ * memory; the argmax over boxes is re-checked in exact fp32 whenever the two best candidates are
+ * within 6e-5, so D_ind is the fp32 pick.  Bound for this path: D_sim / margin_loss within 2e-4
+ * relative (+1e-5 absolute) of the fp32 path.  Nb <= 128.  Two launches (tiles, then the per-segment
+ * phases).  Which form is faster depends on the shape -- profiles/RESULTS.md has the A/B. */
+int nafae_ground_forward_tc(const float* vis_feats, const float* word_feats, const int* entities_length,
+                            int Na, int Ns, int Nb, int Ne, int D, float Delta, float vis_lam, int train,
+                            int64_t* D_ind, float* D_sim, float* margin_loss, void* workspace,
+                            size_t workspace_bytes, cudaStream_t stream);
 int nafae_ground_backward(const float* grad_margin_loss, const float* vis_feats,
                           const float* word_feats, const int* entities_length, int Na, int Ns,
                           int Nb, int Ne, int D, float Delta, float vis_lam, int train,

@@ -58,6 +58,9 @@ SIGNATURES = {
     "nafae_ground_forward_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                              c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nafae_ground_forward_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
     "nafae_ground_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -20,7 +20,7 @@
 //
 // Arithmetic: fp32 FMA, fp32 accumulate.  The contraction is 85 MFLOP at the benchmark shape and
 // latency bound; see DESIGN.md for why it runs on the FMA pipe rather than tcgen05 tiles.
-#include "common.cuh"
+#include "tc05.cuh"
 
 namespace nafae {
 namespace {
@@ -377,6 +377,231 @@ __global__ void __launch_bounds__(kFwdThreads, 1) ground_fwd_kernel(const FwdPar
   phase3_final(p, w);
   TRACE(125);
   if (tid == 0) *w.done_cnt = 0;
+}
+
+// P2 / P3 alone (one CTA per segment): the tail of the forward when P1 ran as the tensor-core kernel
+__global__ void __launch_bounds__(kFwdThreads, 1) ground_p23_kernel(const FwdParams p) {
+  NAFAE_CTA_TRACE(cta_trace, 3);
+  __shared__ int s_ticket;
+  const Dims& d = p.d;
+  const Ws w = ws_carve(p.ws, d);
+  const int a = blockIdx.x;
+  phase2_segment(p, w, a);
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = ticket_acq_rel(w.done_cnt);
+  __syncthreads();
+  if (s_ticket != d.Na - 1) return;
+  phase3_final(p, w);
+  if (threadIdx.x == 0) *w.done_cnt = 0;
+}
+
+// ---------------------------------------------------- P1 on the tensor cores (tcgen05) ----
+// S_ = vis_feats @ word_feats^T (model.py:548) as 128-row tiles of tcgen05.mma, fp32 inputs fed as
+// THREE tf32 products per K step (x = hi + lo with hi = x truncated to tf32, lo = x - hi exactly):
+//     S += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo          (the dropped lo.lo term is ~2^-22 relative)
+// so the accumulator agrees with the fp32 FMA path to ~1e-6 relative instead of tf32's 1e-3, and the
+// argmax over boxes is re-checked in exact fp32 whenever the two best candidates are closer than
+// kTcTieTol -- D_ind stays the fp32 pick.
+//   grid  (row tiles, column tiles): a row tile = floor(128 / Nb) whole frames (so every frame's max
+//         is tile-local), a column tile = up to 128 query columns (TMEM columns of one accumulator)
+//   warp 0      TMA producer: 128 x 32 and NQt x 32 fp32 boxes (128-byte swizzle), 3-stage ring
+//   warps 2-9   split hi / lo in place (element-wise: layout agnostic), then warps 2-5 read the
+//               accumulator from TMEM into a shared S tile and all of them reduce per (frame, column)
+//   warp 1      TMEM allocation + MMA issue (12 tcgen05.mma per stage), tcgen05.commit
+constexpr int kTcThreads = 320;
+constexpr int kTcSplitThreads = 256;
+constexpr int kTcStages = 3;
+constexpr int kTcBK = 32;             // fp32 elements per stage row = 128 bytes
+constexpr float kTcTieTol = 6e-5f;    // absolute gap below which the fp32 re-check decides
+
+struct P1TcParams {
+  const float* vis;
+  const float* word;
+  const int* lens;
+  long long* D_ind;
+  float* D_sim;
+  Dims d;
+  int fpt;    // frames per row tile
+  int nqt;    // columns per column tile (multiple of 16, <= 128)
+};
+
+__device__ __forceinline__ float exact_dot(const float* __restrict__ x, const float* __restrict__ y, int D) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int k = 0; k < D; k += 4) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + k));
+    const float4 yv = __ldg(reinterpret_cast<const float4*>(y + k));
+    a0 = fmaf(xv.x, yv.x, a0);
+    a1 = fmaf(xv.y, yv.y, a1);
+    a2 = fmaf(xv.z, yv.z, a2);
+    a3 = fmaf(xv.w, yv.w, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+ground_p1_tc_kernel(const __grid_constant__ CUtensorMap map_vis, const __grid_constant__ CUtensorMap map_word,
+                    const P1TcParams p) {
+  NAFAE_CTA_TRACE(cta_trace, 3);
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const Dims& d = p.d;
+  const int a_bytes = 128 * 128, b_bytes = p.nqt * 128;
+  const int stage_bytes = 2 * (a_bytes + b_bytes);  // [A hi | A lo | B hi | B lo]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kTcStages * stage_bytes);
+  uint64_t* ready = full + kTcStages;
+  uint64_t* empty = ready + kTcStages;
+  uint64_t* acc_ready = empty + kTcStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+  float* S = reinterpret_cast<float*>(smem);  // epilogue: [128][nqt + 1], reuses the ring
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f0 = blockIdx.x * p.fpt;                       // first frame of the tile
+  const int nf = min(p.fpt, d.F - f0);                     // frames in the tile
+  const int m0 = f0 * d.Nb;                                // first vis row
+  const int c0 = blockIdx.y * p.nqt;                       // first query column
+  const int nc = min(p.nqt, d.NQ - c0);
+  const int nkb = (d.D + kTcBK - 1) / kTcBK;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.nqt) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], kTcSplitThreads);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_ready, 1);
+    fence_mbar_init();
+    tc05::tma_prefetch_desc(&map_vis);
+    tc05::tma_prefetch_desc(&map_word);
+  }
+  if (warp == 1) tc05::tmem_alloc(tmem_slot, tmem_cols);
+  tc05::fence_before_sync();
+  __syncthreads();
+  tc05::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kTcStages;
+        mbar_wait(&empty[s], ((uint32_t)(kb / kTcStages) & 1u) ^ 1u);
+        unsigned char* st = smem + (size_t)s * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], (uint32_t)(a_bytes + b_bytes));
+        tc05::tma_load_2d(st, &map_vis, &full[s], kb * kTcBK, m0);
+        tc05::tma_load_2d(st + 2 * a_bytes, &map_word, &full[s], kb * kTcBK, c0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc05::instr_desc(tc05::kFmtTF32, 128, p.nqt);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kTcStages;
+        mbar_wait(&ready[s], (uint32_t)(kb / kTcStages) & 1u);
+        tc05::fence_after_sync();
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t a_hi = tc05::smem_desc_sw128(st), a_lo = tc05::smem_desc_sw128(st + a_bytes);
+        const uint64_t b_hi = tc05::smem_desc_sw128(st + 2 * a_bytes);
+        const uint64_t b_lo = tc05::smem_desc_sw128(st + 2 * a_bytes + b_bytes);
+#pragma unroll
+        for (int k = 0; k < kTcBK / 8; ++k) {  // 8 tf32 = 32 bytes of K per instruction
+          const uint64_t o = (uint64_t)(2 * k);
+          tc05::mma_tf32(tmem_base, a_hi + o, b_hi + o, idesc, (kb | k) != 0);
+          tc05::mma_tf32(tmem_base, a_lo + o, b_hi + o, idesc, 1u);
+          tc05::mma_tf32(tmem_base, a_hi + o, b_lo + o, idesc, 1u);
+        }
+        tc05::commit(&empty[s]);
+      }
+      tc05::commit(acc_ready);
+    }
+  } else {
+    // ---- hi / lo split of every landed stage (256 threads), element-wise in place
+    const int t = tid - 64;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kTcStages;
+      mbar_wait(&full[s], (uint32_t)(kb / kTcStages) & 1u);
+      unsigned char* st = smem + (size_t)s * stage_bytes;
+      auto split = [&](unsigned char* hi_base, int bytes) {
+        uint4* hi = reinterpret_cast<uint4*>(hi_base);
+        uint4* lo = reinterpret_cast<uint4*>(hi_base + bytes);
+        for (int i = t; i < bytes / 16; i += kTcSplitThreads) {
+          const uint4 x = hi[i];
+          uint4 h, l;
+          h.x = x.x & 0xffffe000u; h.y = x.y & 0xffffe000u; h.z = x.z & 0xffffe000u; h.w = x.w & 0xffffe000u;
+          l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
+          hi[i] = h;
+          lo[i] = l;
+        }
+      };
+      split(st, a_bytes);
+      split(st + 2 * a_bytes, b_bytes);
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async reads
+      mbar_arrive(&ready[s]);
+    }
+    // ---- epilogue: accumulator -> shared S tile (warps 2..5 own TMEM lane quarters 2, 3, 0, 1)
+    mbar_wait(acc_ready, 0);
+    tc05::fence_after_sync();
+    const int ld = p.nqt + 1;
+    if (warp < 6) {
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      for (int cc = 0; cc < p.nqt; cc += 32) {
+        uint32_t v[32];
+        tc05::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cc + j < p.nqt) S[row * ld + cc + j] = __uint_as_float(v[j]);
+      }
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(kTcSplitThreads) : "memory");  // the 8 split / epilogue warps
+    // ---- per (frame, column): max / first argmax over the Nb boxes (model.py:608-612), masked
+    // columns are all-zero after masked_fill_ (model.py:551): max 0 at index 0
+    for (int i = t; i < nf * nc; i += kTcSplitThreads) {
+      const int fl = i / nc, c = c0 + i % nc;
+      const bool live = (c % d.Ne) < __ldg(p.lens + c / d.Ne);
+      float best = 0.f;
+      int bi = 0;
+      if (live) {
+        const float* col = S + (size_t)(fl * d.Nb) * ld + (c - c0);
+        best = -INFINITY;
+        float second = -INFINITY;
+        for (int r = 0; r < d.Nb; ++r) {
+          const float x = col[(size_t)r * ld];
+          if (x > best) {
+            second = best;
+            best = x;
+            bi = r;
+          } else if (x > second) {
+            second = x;
+          }
+        }
+        if (best - second < kTcTieTol) {  // too close for the tf32x3 accumulator: decide in fp32
+          const float* wrow = p.word + (size_t)c * d.D;
+          float eb = -INFINITY;
+          int ei = 0;
+          for (int r = 0; r < d.Nb; ++r)
+            if (best - col[(size_t)r * ld] < 2.f * kTcTieTol) {
+              const float e = exact_dot(p.vis + (size_t)(m0 + fl * d.Nb + r) * d.D, wrow, d.D);
+              if (e > eb) {
+                eb = e;
+                ei = r;
+              }
+            }
+          best = eb;
+          bi = ei;
+        }
+      }
+      p.D_sim[(size_t)(f0 + fl) * d.NQ + c] = best;
+      p.D_ind[(size_t)(f0 + fl) * d.NQ + c] = (long long)bi;
+    }
+  }
+  tc05::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc05::tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // Column statistics of one segment from a shared-memory copy of its D_sim block.
@@ -1313,4 +1538,82 @@ NAFAE_API int nafae_eval_record(const int64_t* D_ind, const float* D_sim, const 
       reinterpret_cast<long long*>(out_box_rows), out_boxes, out_confs, gt_boxes, gt_classes, gt_thr,
       num_classes, class_match, class_count);
   return launch_status("eval_record_kernel");
+}
+
+// Same contract as nafae_ground_forward; the region x query contraction runs on the tensor cores
+// (tf32 x 3, fp32-rechecked picks), P2 / P3 follow in a second launch.
+NAFAE_API int nafae_ground_forward_tc(const float* vis_feats, const float* word_feats,
+                                      const int* entities_length, int Na, int Ns, int Nb, int Ne, int D,
+                                      float Delta, float vis_lam, int train, int64_t* D_ind, float* D_sim,
+                                      float* margin_loss, void* workspace, size_t workspace_bytes,
+                                      cudaStream_t stream) {
+  Dims d;
+  NAFAE_REQUIRE(make_dims(Na, Ns, Nb, Ne, D, &d), "ground: sizes must be positive");
+  if (check_ground_args(d, workspace, workspace_bytes, train) != 1) return 0;
+  NAFAE_REQUIRE(vis_feats && word_feats && entities_length && D_ind && D_sim && margin_loss,
+                "ground: NULL buffer");
+  NAFAE_REQUIRE(((reinterpret_cast<uintptr_t>(vis_feats) | reinterpret_cast<uintptr_t>(word_feats)) & 15) == 0,
+                "ground_tc: vis_feats / word_feats must be 16-byte aligned");
+  NAFAE_REQUIRE(Nb <= 128, "ground_tc: at most 128 boxes per frame (got %d); use nafae_ground_forward", Nb);
+  NAFAE_REQUIRE(D % 4 == 0, "ground_tc: D must be a multiple of 4");
+  P1TcParams q;
+  q.vis = vis_feats;
+  q.word = word_feats;
+  q.lens = entities_length;
+  q.D_ind = reinterpret_cast<long long*>(D_ind);
+  q.D_sim = D_sim;
+  q.d = d;
+  q.fpt = 128 / Nb;
+  int nqt = (d.NQ + 15) / 16 * 16;  // columns per tile: 3 ring stages of [A hi|A lo|B hi|B lo] must fit
+  if (nqt > 128) nqt = 128;
+  q.nqt = nqt;
+  CUtensorMap mv, mw;
+  if (!tc05::make_tensor_map_2d(&mv, vis_feats, 4, false, (long long)d.F * Nb, D, 128)) return 0;
+  if (!tc05::make_tensor_map_2d(&mw, word_feats, 4, false, d.NQ, D, nqt)) return 0;
+  const size_t ring = (size_t)kTcStages * 2 * (128 * 128 + (size_t)nqt * 128);
+  const size_t stile = (size_t)128 * (nqt + 1) * 4;
+  const size_t smem_tc = 1024 + (ring > stile ? ring : stile) + 256;
+  NAFAE_REQUIRE(smem_tc <= 227 * 1024, "ground_tc: shared memory");
+  cudaError_t e = cudaFuncSetAttribute(ground_p1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_tc);
+  if (e != cudaSuccess) {
+    set_error("ground_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return -(int)e;
+  }
+  dim3 grid(ceil_div(d.F, q.fpt), ceil_div(d.NQ, nqt));
+  ground_p1_tc_kernel<<<grid, kTcThreads, smem_tc, stream>>>(mv, mw, q);
+  int st = launch_status("ground_p1_tc_kernel");
+  if (st != 1) return st;
+  FwdParams p;
+  p.vis = vis_feats;
+  p.word = word_feats;
+  p.lens = entities_length;
+  p.D_ind = reinterpret_cast<long long*>(D_ind);
+  p.D_sim = D_sim;
+  p.loss = margin_loss;
+  p.ws = workspace;
+  p.d = d;
+  p.Delta = Delta;
+  p.vis_lam = vis_lam;
+  p.train = train ? 1 : 0;
+  p.col_chunks = 1;
+  p.groups = 1;
+  p.ws_group_bytes = 0;
+  size_t smem = (size_t)kRowTile * d.D * 4;
+  const size_t p2 = ((size_t)(train ? (d.Nb < kRowTile ? d.Nb : kRowTile) : 0) * d.D +
+                     (size_t)2 * d.Ns * d.NQ + 2 * (size_t)d.NQ + (size_t)(d.Nb > kRowTile ? d.Nb : kRowTile) +
+                     (size_t)kRowTile * kRowTile) * 4;
+  const size_t p3 = (size_t)d.Na * d.Ns * d.Na * 4;
+  if (p2 > smem) smem = p2;
+  if (p3 > smem) smem = p3;
+  NAFAE_REQUIRE(smem <= 200 * 1024, "ground: D=%d / Ns=%d need too much shared memory", d.D, d.Ns);
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(ground_p23_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("ground: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return -(int)e;
+    }
+  }
+  ground_p23_kernel<<<d.Na, kFwdThreads, smem, stream>>>(p);
+  return launch_status("ground_p23_kernel");
 }

@@ -284,9 +284,6 @@ struct SlabParams {
   int* gate;       // optional residency gate (nafae_gate_wait): [0] arrivals, [1] epoch
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void cons_barrier() {  // the 16 consumer warps only
   asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory");
 }

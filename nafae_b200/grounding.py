@@ -16,7 +16,7 @@ from . import _C
 
 class _Ground(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, vis_feats, word_feats, lens, dims, Delta, vis_lam, train, pool, recording):
+    def forward(ctx, vis_feats, word_feats, lens, dims, Delta, vis_lam, train, pool, recording, tensor_cores):
         Na, Ns, Nb, Ne, D = dims
         vis = _C.f32c(vis_feats, "vis_feats")
         word = _C.f32c(word_feats, "word_feats")
@@ -29,12 +29,12 @@ class _Ground(torch.autograd.Function):
         D_sim = torch.empty((F, NQ), dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         ws = pool.take(dims, dev)
+        fwd = _C.lib.nafae_ground_forward_tc if tensor_cores else _C.lib.nafae_ground_forward
         with torch.cuda.device(dev):
-            st = _C.lib.nafae_ground_forward(_C.ptr(vis), _C.ptr(word), _C.ptr(lens), Na, Ns, Nb,
-                                             Ne, D, float(Delta), float(vis_lam), int(train),
-                                             _C.ptr(D_ind), _C.ptr(D_sim), _C.ptr(loss),
-                                             _C.ptr(ws), ws.numel() * 4, _C.stream(dev))
-        _C.check(st, "nafae_ground_forward")
+            st = fwd(_C.ptr(vis), _C.ptr(word), _C.ptr(lens), Na, Ns, Nb, Ne, D, float(Delta), float(vis_lam),
+                     int(train), _C.ptr(D_ind), _C.ptr(D_sim), _C.ptr(loss), _C.ptr(ws), ws.numel() * 4,
+                     _C.stream(dev))
+        _C.check(st, "nafae_ground_forward_tc" if tensor_cores else "nafae_ground_forward")
         # a backward can only follow when a graph is being recorded (`recording` = the caller's
         # torch.is_grad_enabled(); inside Function.forward grad mode is always off): under
         # torch.no_grad() -- the usual validation loop over live modules -- the workspace goes
@@ -73,7 +73,7 @@ class _Ground(torch.autograd.Function):
         _C.check(st, "nafae_ground_backward")
         ctx.pool.give((Na, Ns, Nb, Ne, D), dev, ws)
         ctx.ws = None
-        return gvis, gword, None, None, None, None, None, None, None
+        return gvis, gword, None, None, None, None, None, None, None, None
 
 
 class _WorkspacePool(object):
@@ -100,9 +100,12 @@ def _lens_tensor(entities_length, device):
     return torch.tensor([int(x) for x in entities_length], dtype=torch.int32, device=device)
 
 
-def ground(vis_feats, word_feats, entities_length, Na, Nb, Ne, Delta, vis_lam, train, pool=None):
+def ground(vis_feats, word_feats, entities_length, Na, Nb, Ne, Delta, vis_lam, train, pool=None,
+           tensor_cores=False):
     """Functional form.  ``entities_length``: list of ints (as in the reference) or an int32 CUDA
-    tensor (no H2D copy).  Returns (D_ind int64 (Na*Ns, Na*Ne), D_sim f32, margin_loss 0-dim)."""
+    tensor (no H2D copy).  Returns (D_ind int64 (Na*Ns, Na*Ne), D_sim f32, margin_loss 0-dim).
+    ``tensor_cores``: run the regions x queries contraction as tcgen05 tf32x3 tiles
+    (`nafae_ground_forward_tc`: same picks, D_sim / loss within 2e-4 relative)."""
     _C.require_cuda(vis_feats, "vis_feats")
     Ns = int(vis_feats.size(0) / Na / Nb)  # model.py:530
     dims = (int(Na), Ns, int(Nb), int(Ne), int(vis_feats.size(1)))
@@ -110,7 +113,8 @@ def ground(vis_feats, word_feats, entities_length, Na, Nb, Ne, Delta, vis_lam, t
     if lens.numel() != Na:
         raise ValueError("entities_length must have Na=%d entries" % Na)
     return _Ground.apply(vis_feats, word_feats, lens, dims, Delta, vis_lam, train,
-                         pool if pool is not None else _DEFAULT_POOL, torch.is_grad_enabled())
+                         pool if pool is not None else _DEFAULT_POOL, torch.is_grad_enabled(),
+                         bool(tensor_cores))
 
 
 _DEFAULT_POOL = _WorkspacePool()
@@ -132,6 +136,7 @@ class DVSA(torch.nn.Module):
         self.args = args
         self.cfg = cfg
         self.phase = ''
+        self.tensor_cores = bool(getattr(args, "tensor_cores", False))  # tcgen05 form of the contraction
         self._pool = _WorkspacePool()
 
     def init_train(self):
@@ -147,7 +152,8 @@ class DVSA(torch.nn.Module):
             raise RuntimeError("call init_train() or init_eval() first (model.py:509-515)")
         Nb = self.cfg.TEST.RPN_POST_NMS_TOP_N
         return ground(vis_feats, word_feats, entities_length, self.Na, Nb, self.args.max_ent_len,
-                      self.args.Delta, self.args.vis_lam, self.phase == 'train', self._pool)
+                      self.args.Delta, self.args.vis_lam, self.phase == 'train', self._pool,
+                      self.tensor_cores)
 
 
 def postprocess(D, D_sim, Na, Ns, Nb, Ne):

@@ -19,7 +19,7 @@ class GroundingStep(object):
 
     def __init__(self, Na, Ns, Nb, Ne, D, C, H, W, n_props, pre_nms_topn=6000, nms_thresh=0.7,
                  spatial_scale=1.0 / 16.0, Delta=10.0, vis_lam=4.13, train=True, device=None,
-                 l1_loss=True):
+                 l1_loss=True, tensor_cores=False):
         self.dev = torch.device(device if device is not None else
                                 "cuda:%d" % torch.cuda.current_device())
         self.dims = (Na, Ns, Nb, Ne, D)
@@ -27,6 +27,7 @@ class GroundingStep(object):
         self.C, self.H, self.W, self.n = C, H, W, n_props
         self.pre, self.thresh, self.scale = int(pre_nms_topn), float(nms_thresh), float(spatial_scale)
         self.Delta, self.vis_lam, self.train = float(Delta), float(vis_lam), bool(train)
+        self.tensor_cores = bool(tensor_cores)  # contraction of the scoring kernel on tcgen05 (tf32x3)
         f32 = dict(dtype=torch.float32, device=self.dev)
         # device-resident inputs
         self.features = torch.empty((self.F, C, H, W), **f32)
@@ -127,7 +128,8 @@ class GroundingStep(object):
         s = _C.stream(self.dev)
         do_bwd = self.train if backward is None else backward
         with torch.cuda.device(self.dev):
-            _C.check(L.nafae_ground_forward(P(self.vis_feats), P(self.word_feats), P(self.lens),
+            fwd = L.nafae_ground_forward_tc if self.tensor_cores else L.nafae_ground_forward
+            _C.check(fwd(P(self.vis_feats), P(self.word_feats), P(self.lens),
                                             Na, Ns, Nb, Ne, D, self.Delta, self.vis_lam,
                                             int(self.train), P(self.D_ind), P(self.D_sim),
                                             P(self.loss), P(self.ws), self.ws.numel() * 4, s),

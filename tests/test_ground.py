@@ -160,3 +160,63 @@ def test_no_grad_forward_returns_the_workspace_and_second_backward_is_a_clear_er
     assert vis.grad is not None and sum(len(v) for v in pool._free.values()) == 1
     with pytest.raises(RuntimeError, match="second backward"):
         loss.backward()
+
+
+@gpu
+@pytest.mark.parametrize("Na,Ns,Nb,Ne,D,train", [
+    (8, 5, 20, 13, 512, True),      # cfg2
+    (1, 32, 100, 13, 512, False),   # cfg4: one frame per 128-row tile
+    (3, 4, 7, 5, 64, True),         # small, ragged tiles (18 frames of 7 rows per tile)
+    (24, 2, 20, 13, 512, False),    # 312 query columns: three column tiles
+])
+def test_tensor_core_contraction_matches_the_fp32_path(Na, Ns, Nb, Ne, D, train):
+    """nafae_ground_forward_tc (tcgen05, tf32 x 3) vs nafae_ground_forward (fp32 FMA): identical picks
+    on every live column, D_sim / margin_loss within the looser tensor-core bound (2e-4 relative,
+    1e-5 absolute), and gradients from the shared backward agree to the same bound."""
+    from nafae_b200.grounding import ground
+    dev = torch.device("cuda:0")
+    rs = np.random.RandomState(Na * 31 + Nb)
+    vis = torch.from_numpy(synth.embeddings(rs, Na * Ns * Nb, D)).to(dev)
+    word = torch.from_numpy(synth.embeddings(rs, Na * Ne, D)).to(dev)
+    lens = [int(x) for x in rs.randint(0, Ne + 1, Na)]
+    lens[0] = max(lens[0], 1)
+    # exact ties and near ties: duplicate a box row inside a frame, and a copy that differs by 1 ulp
+    vis[1] = vis[0]
+    vis[2] = vis[0] * (1 + 2 ** -22)
+    outs = []
+    for tc in (False, True):
+        v = vis.clone().requires_grad_(train)
+        w = word.clone().requires_grad_(train)
+        D_ind, D_sim, loss = ground(v, w, lens, Na, Nb, Ne, 10.0, 4.13, train, tensor_cores=tc)
+        if train:
+            loss.backward()
+        torch.cuda.synchronize()
+        outs.append((D_ind, D_sim, loss.detach(), v.grad, w.grad))
+    live = np.zeros((Na, Ne), bool)
+    for a, n in enumerate(lens):
+        live[a, :n] = True
+    live = torch.from_numpy(live.reshape(-1)).to(dev)
+    assert torch.equal(outs[0][0][:, live], outs[1][0][:, live])
+    assert torch.equal(outs[1][0][:, ~live], torch.zeros_like(outs[1][0][:, ~live]))
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=2e-4, atol=1e-5)
+    assert torch.allclose(outs[0][2], outs[1][2], rtol=2e-4, atol=1e-5)
+    if train:
+        for g0, g1 in ((outs[0][3], outs[1][3]), (outs[0][4], outs[1][4])):
+            assert torch.allclose(g0, g1, rtol=2e-4, atol=2e-4 * float(g0.abs().max()))
+
+
+@gpu
+@pytest.mark.parametrize("name", ["cfg2_train", "ties_train", "cfg4_eval"])
+def test_tensor_core_path_matches_the_reference_fixture(name):
+    """The tensor-core forward against the reference's own DVSA outputs (tests/golden/dvsa_*.npz),
+    including the fixture whose frames hold duplicated box rows (exact ties -> first index)."""
+    case, z = load_dvsa_case(name)
+    vis, word = dvsa_inputs(case)
+    from nafae_b200.grounding import ground
+    dev = torch.device("cuda:0")
+    D_ind, D_sim, loss = ground(torch.from_numpy(vis).to(dev), torch.from_numpy(word).to(dev), case["lens"],
+                                case["Na"], case["Nb"], case["Ne"], case["Delta"], case["vis_lam"],
+                                case["phase"] == "train", tensor_cores=True)
+    np.testing.assert_array_equal(D_ind.cpu().numpy(), z["D_ind"])  # all columns, masked ones included
+    np.testing.assert_allclose(D_sim.cpu().numpy(), z["D_sim"], rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(float(loss), float(z["margin_loss"]), rtol=2e-4)
