@@ -41,6 +41,9 @@ typedef struct CUstream_st* cudaStream_t; /* same opaque handle as CUDA driver_t
 /* flags */
 #define NAFAE_FLAG_NO_GATE 2u /* nafae_roi_align_forward: ignore the workspace's residency gate --
                                  nobody waits on this launch (keeps gate epochs paired with waiters) */
+#define NAFAE_FLAG_OUT_BF16 4u /* nafae_roi_align_forward: top_data is bf16 -- the (R, C*7*7) row-major
+                                  A operand of the bridge GEMM (nafae_gemm_bf16_tn) written directly,
+                                  half the output bytes; bandwidth-kernel shapes only */
 #define NAFAE_FLAG_EXACT 1u /* reference-order arithmetic (mixed fp32/fp64 exactly as the
                                reference kernel evaluates it): bit-identical pooled features,
                                slower.  Default (0) = fp32 FMA path, <= 1e-4 relative. */
@@ -146,7 +149,7 @@ size_t nafae_roi_align_workspace_bytes(int batch_size, int num_rois);
 int nafae_roi_align_persistent_ctas(int num_units);
 int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size,
                             int num_rois, int height, int width, int channels, int out_height,
-                            int out_width, int pool_mode, const float* bottom_rois, float* top_data,
+                            int out_width, int pool_mode, const float* bottom_rois, void* top_data,
                             unsigned flags, void* workspace, size_t workspace_bytes,
                             cudaStream_t stream);
 

@@ -110,6 +110,7 @@ if not MISSING and int(lib.nafae_abi_version()) != ABI_VERSION:
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 FLAG_EXACT = 1
 FLAG_NO_GATE = 2
+FLAG_OUT_BF16 = 4
 GATE_BYTES = 32
 ROI_ALIGN_WS_BYTES = 64
 

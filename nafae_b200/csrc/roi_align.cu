@@ -25,6 +25,10 @@
 //       3-stage ring; every feature byte is read from HBM exactly once, all RoIs of the frame
 //       are served from shared memory, the (R,C,8,8) intermediate never exists, and the 2x2
 //       pool is a register/shuffle epilogue.
+#include <cuda_bf16.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace nafae {
@@ -272,7 +276,7 @@ struct __align__(16) RoiEntry {  // 192 B: everything a pass needs about one RoI
 struct SlabParams {
   const float* bottom;
   const float* rois;
-  float* top;
+  void* top;       // (R, C, 7, 7) fp32, or bf16 (NAFAE_FLAG_OUT_BF16)
   float scale;
   int B, R, H, W, C;
   int cg;          // channels per slab
@@ -288,8 +292,14 @@ __device__ __forceinline__ void cons_barrier() {  // the 16 consumer warps only
   asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory");
 }
 
-template <int POOL, int W_CT, int HWP_CT, int CPL, int NBLK_CT>
+template <int POOL, int W_CT, int HWP_CT, int CPL, int NBLK_CT, bool BF16>
 __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const SlabParams p) {
+  using OutT = typename std::conditional<BF16, __nv_bfloat16, float>::type;
+  auto to_out = [](float v) -> OutT {
+    if constexpr (BF16) return __float2bfloat16_rn(v);
+    else return v;
+  };
+  OutT* const top = static_cast<OutT*>(p.top);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: [stages][cg][hwp] floats | RoiEntry[kMaxRoiTable] | int roi_id[kMaxRoiTable] | bars |
   //         per-warp output staging
@@ -301,7 +311,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
   int* roi_id = reinterpret_cast<int*>(table + kMaxRoiTable);
   uint64_t* full = reinterpret_cast<uint64_t*>(roi_id + kMaxRoiTable);
   uint64_t* empty = full + kStagesMax;
-  float* out_stage = reinterpret_cast<float*>(empty + kStagesMax);  // [kConsWarps][4*CPL][7][7]
+  OutT* out_stage = reinterpret_cast<OutT*>(empty + kStagesMax);  // [kConsWarps][4*CPL][7][7]
   __shared__ int s_nroi, s_next, s_warp_cnt[kConsWarps], s_fbeg[kPreFrames + 1];
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -368,8 +378,8 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
       while (bad) {
         const int rr = base + warp * 32 + __ffs(bad) - 1;
         bad &= bad - 1;
-        float* o = p.top + (size_t)rr * p.C * (kOut * kOut);
-        for (int i = lane; i < p.C * kOut * kOut; i += 32) o[i] = 0.f;
+        OutT* o = top + (size_t)rr * p.C * (kOut * kOut);
+        for (int i = lane; i < p.C * kOut * kOut; i += 32) o[i] = to_out(0.f);
       }
     };
     if (fr_cached) {
@@ -492,7 +502,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
   const int nblk = NBLK_CT ? NBLK_CT : p.cg / (4 * CPL);
   const int cq = lane >> 3, pw = lane & 7;
   int g_base = 0;  // running pass-group counter (uniform): deals groups round-robin to warps
-  float* my_stage = out_stage + warp * (4 * CPL * kOut * kOut);
+  OutT* my_stage = out_stage + warp * (4 * CPL * kOut * kOut);
   for (int u = u_begin; u < u_end; ++u) {
     const int it = u - u_begin;
     const int stage = it % p.stages;
@@ -594,16 +604,16 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
         // pooled block -> per-warp staging (channel-major like the output) -> one bulk store
         if (lane == 0) bulk_wait_read<0>();  // the previous pass's store has drained the buffer
         __syncwarp();
-        float* o = my_stage + cq * (kOut * kOut) + pw;
+        OutT* o = my_stage + cq * (kOut * kOut) + pw;
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
-          float* ok = o + k * 4 * (kOut * kOut);
+          OutT* ok = o + k * 4 * (kOut * kOut);
           if (POOL == NAFAE_POOL_AVG) {
             float hs_prev = s[k][0] + __shfl_down_sync(0xffffffffu, s[k][0], 1);
 #pragma unroll
             for (int i = 0; i < kOut; ++i) {
               const float hs = s[k][i + 1] + __shfl_down_sync(0xffffffffu, s[k][i + 1], 1);
-              if (pw < kOut) ok[i * kOut] = hs_prev + hs;
+              if (pw < kOut) ok[i * kOut] = to_out(hs_prev + hs);
               hs_prev = hs;
             }
           } else {
@@ -612,7 +622,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
             for (int i = 0; i < kOut; ++i) {
               const float right_next = __shfl_down_sync(0xffffffffu, s[k][i + 1], 1);
               const float v = pool4(POOL, s[k][i], right_prev, s[k][i + 1], right_next);
-              if (pw < kOut) ok[i * kOut] = v;
+              if (pw < kOut) ok[i * kOut] = to_out(v);
               right_prev = right_next;
             }
           }
@@ -621,8 +631,8 @@ __global__ void __launch_bounds__(kSlabThreads, 1) align_pool_fwd_slab(const Sla
         __syncwarp();
         if (lane == 0) {
           const int c_first = gidx * p.cg + blk * (4 * CPL);
-          bulk_s2g(p.top + ((size_t)roi_id[j] * p.C + c_first) * (kOut * kOut), my_stage,
-                   (uint32_t)(4 * CPL * kOut * kOut * sizeof(float)));
+          bulk_s2g(top + ((size_t)roi_id[j] * p.C + c_first) * (kOut * kOut), my_stage,
+                   (uint32_t)(4 * CPL * kOut * kOut * sizeof(OutT)));
           bulk_commit();
         }
       }
@@ -661,9 +671,12 @@ int slab_grid(int units) {
 }
 
 template <int W_CT, int HWP_CT, int CPL, int NBLK_CT>
-int launch_slab(const SlabParams& p, int pool, size_t smem, cudaStream_t stream) {
-  auto kern = pool == NAFAE_POOL_AVG ? align_pool_fwd_slab<NAFAE_POOL_AVG, W_CT, HWP_CT, CPL, NBLK_CT>
-                                     : align_pool_fwd_slab<NAFAE_POOL_MAX, W_CT, HWP_CT, CPL, NBLK_CT>;
+int launch_slab(const SlabParams& p, int pool, bool bf16, size_t smem, cudaStream_t stream) {
+  auto kern = pool == NAFAE_POOL_AVG
+                  ? (bf16 ? align_pool_fwd_slab<NAFAE_POOL_AVG, W_CT, HWP_CT, CPL, NBLK_CT, true>
+                          : align_pool_fwd_slab<NAFAE_POOL_AVG, W_CT, HWP_CT, CPL, NBLK_CT, false>)
+                  : (bf16 ? align_pool_fwd_slab<NAFAE_POOL_MAX, W_CT, HWP_CT, CPL, NBLK_CT, true>
+                          : align_pool_fwd_slab<NAFAE_POOL_MAX, W_CT, HWP_CT, CPL, NBLK_CT, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("roi_align: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
@@ -677,7 +690,7 @@ int launch_slab(const SlabParams& p, int pool, size_t smem, cudaStream_t stream)
 // Returns 1 if the slab kernel was launched, 0 if the shape is not eligible (caller falls back),
 // <0 on a launch error.
 int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W, int C, int pool,
-                    const float* rois, float* top, int* gate, cudaStream_t stream) {
+                    const float* rois, void* top, bool bf16, int* gate, cudaStream_t stream) {
   const int hw = H * W;
   if (hw % 4 != 0 || C % 8 != 0 || H < 2 || W < 2) return 0;
   if ((reinterpret_cast<uintptr_t>(bottom) & 15) != 0) return 0;
@@ -724,9 +737,9 @@ int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W
   p.units = B * p.groups;
   p.gate = gate;
   const size_t smem = (size_t)cg * hwp * 4 * stages + fixed;
-  if (W == 50 && hwp == 1928 && cg == 8) return launch_slab<50, 1928, 2, 1>(p, pool, smem, stream);  // 38x50
-  if (small_map && cg == 32) return launch_slab<14, 200, 4, 2>(p, pool, smem, stream);                // 14x14
-  return launch_slab<0, 0, 2, 0>(p, pool, smem, stream);
+  if (W == 50 && hwp == 1928 && cg == 8) return launch_slab<50, 1928, 2, 1>(p, pool, bf16, smem, stream);  // 38x50
+  if (small_map && cg == 32) return launch_slab<14, 200, 4, 2>(p, pool, bf16, smem, stream);                // 14x14
+  return launch_slab<0, 0, 2, 0>(p, pool, bf16, smem, stream);
 }
 
 int grid_for(long long total) {
@@ -756,7 +769,7 @@ NAFAE_API size_t nafae_roi_align_workspace_bytes(int batch_size, int num_rois) {
 NAFAE_API int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size,
                                       int num_rois, int height, int width, int channels,
                                       int out_height, int out_width, int pool_mode,
-                                      const float* bottom_rois, float* top_data, unsigned flags,
+                                      const float* bottom_rois, void* top_data, unsigned flags,
                                       void* workspace, size_t workspace_bytes,
                                       cudaStream_t stream) {
   NAFAE_REQUIRE(workspace == nullptr || workspace_bytes == 0 ||
@@ -778,22 +791,26 @@ NAFAE_API int nafae_roi_align_forward(const float* bottom_data, float spatial_sc
   NAFAE_REQUIRE(height >= 2 && width >= 2, "roi_align: feature map must be at least 2x2");
   NAFAE_REQUIRE(bottom_data && bottom_rois && top_data, "roi_align: NULL buffer");
   const bool exact = (flags & NAFAE_FLAG_EXACT) != 0;
+  const bool bf16 = (flags & NAFAE_FLAG_OUT_BF16) != 0;
+  NAFAE_REQUIRE(!(bf16 && exact), "roi_align: NAFAE_FLAG_OUT_BF16 and NAFAE_FLAG_EXACT exclude each other");
   if (!exact && pool_mode != NAFAE_POOL_NONE && out_height == kOut && out_width == kOut &&
       batch_size > 0) {
     const int st = try_launch_slab(bottom_data, spatial_scale, batch_size, num_rois, height, width,
-                                   channels, pool_mode, bottom_rois, top_data, gate, stream);
+                                   channels, pool_mode, bottom_rois, top_data, bf16, gate, stream);
     if (st != 0) return st;
   }
+  NAFAE_REQUIRE(!bf16, "roi_align: bf16 output needs the bandwidth kernel's shapes (7x7 avg / max pooling, "
+                       "H*W %% 4 == 0, C %% 8 == 0, 16-byte aligned buffers)");
   if (gate) gate_open(gate, stream);  // no persistent kernel on this path: nothing to wait for
   const int grid = grid_for(total);
   if (exact)
     align_fwd_generic<true><<<grid, 256, 0, stream>>>(bottom_data, spatial_scale, batch_size, total,
                                                       height, width, channels, out_height,
-                                                      out_width, pool_mode, bottom_rois, top_data);
+                                                      out_width, pool_mode, bottom_rois, static_cast<float*>(top_data));
   else
     align_fwd_generic<false><<<grid, 256, 0, stream>>>(bottom_data, spatial_scale, batch_size,
                                                        total, height, width, channels, out_height,
-                                                       out_width, pool_mode, bottom_rois, top_data);
+                                                       out_width, pool_mode, bottom_rois, static_cast<float*>(top_data));
   return launch_status("align_fwd_generic");
 }
 

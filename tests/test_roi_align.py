@@ -292,3 +292,29 @@ def test_persistent_grid_size_and_gate_workspace_do_not_change_results(name, F, 
             assert torch.equal(run(None), base), (name, ctas, "no workspace")
     finally:
         _C.lib.nafae_set_reserved_sms(prev)
+
+
+@gpu
+@pytest.mark.parametrize("F,C,H,W,Nb", [(6, 64, 38, 50, 20), (5, 64, 14, 14, 20)])
+def test_bf16_output_is_the_rounded_fp32_output(F, C, H, W, Nb):
+    """NAFAE_FLAG_OUT_BF16: the bandwidth kernel writes the bridge GEMM's A operand directly --
+    (R, C*7*7) row-major bf16 -- and it is exactly the fp32 result rounded to nearest."""
+    from nafae_b200 import _C
+    rs = np.random.RandomState(F + C)
+    feat = _t(synth.conv5_maps(rs, F, C, H, W) - 0.3)
+    rois = _t(_frame_rois(rs, F, [Nb] * F, H * 16, W * 16))
+    R = rois.shape[0]
+    outs = []
+    for flags, dt in ((0, torch.float32), (_C.FLAG_OUT_BF16, torch.bfloat16)):
+        out = torch.full((R, C, 7, 7), float("nan"), dtype=dt, device=_dev())
+        st = _C.lib.nafae_roi_align_forward(_C.ptr(feat), 1 / 16., F, R, H, W, C, 7, 7, _C.POOL_AVG, _C.ptr(rois),
+                                            _C.ptr(out), flags, None, 0, _C.stream())
+        assert st == 1, _C.last_error()
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[1], outs[0].to(torch.bfloat16))
+    # shapes the bandwidth kernel cannot take have no bf16 form: an argument error, not a silent cast
+    odd = torch.zeros((2, 6, 37, 50), device=_dev())
+    out = torch.zeros((R, 6, 7, 7), dtype=torch.bfloat16, device=_dev())
+    assert _C.lib.nafae_roi_align_forward(_C.ptr(odd), 1 / 16., 2, R, 37, 50, 6, 7, 7, _C.POOL_AVG, _C.ptr(rois),
+                                          _C.ptr(out), _C.FLAG_OUT_BF16, None, 0, _C.stream()) == 0
