@@ -104,6 +104,26 @@ int nafae_nms_batched(int* keep_out, int* num_out, const float* boxes, int num_f
                       int boxes_num, int boxes_dim, float nms_overlap_thresh, void* workspace,
                       size_t workspace_bytes, cudaStream_t stream);
 
+/* Replaces the part of _ProposalLayer.forward BEFORE its per-frame loop --
+ * lib/model/rpn/proposal_layer.py:66-125: anchor enumeration (base windows of generate_anchors.py +
+ * feature-stride shifts, :80-93), the (H, W, A) re-ordering of the NCHW RPN outputs (:98-103),
+ * bbox_transform_inv (lib/model/rpn/bbox_transform.py:77-103), clip_boxes (:125-133) and the per-frame
+ * torch.sort(scores, 1, True) (:125) -- in two launches for the whole batch.
+ *   rpn_cls_prob (B, 2A, H, W): channels [A, 2A) are the foreground probabilities (:66)
+ *   rpn_bbox_pred (B, 4A, H, W); im_info (B, 3) = [height, width, scale] DEVICE; anchors (A, 4) DEVICE
+ *   = generate_anchors(scales, ratios) as float32
+ * Outputs, ready for nafae_proposal_tail: proposals_sorted (B, m, 4) and scores_sorted (B, m) in
+ * score-descending order per frame, m = pre_nms_topn when 0 < pre_nms_topn < B*H*W*A (the reference
+ * compares with the element count of the whole batch, :139) and < H*W*A, else H*W*A; order (B, m) int32
+ * = the anchor index (h*W*A + w*A + a) of every sorted position, or NULL.  Equal scores keep ascending
+ * anchor index (a stable sort; the reference leaves their order unspecified).  H*W*A <= 25600 (the sort
+ * lives in shared memory).  workspace: nafae_proposal_front_workspace_bytes(...) bytes. */
+size_t nafae_proposal_front_workspace_bytes(int batch_size, int num_anchors, int height, int width);
+int nafae_proposal_front(const float* rpn_cls_prob, const float* rpn_bbox_pred, const float* im_info,
+                         const float* anchors, int batch_size, int num_anchors, int height, int width,
+                         float feat_stride, int pre_nms_topn, float* proposals_sorted, float* scores_sorted,
+                         int* order, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* Replaces the per-frame Python loop of _ProposalLayer.forward --
  * lib/model/rpn/proposal_layer.py:127-163 (slice to pre_nms_topN :139-140, nms() :150, first
  * post_nms_topN keeps :154-155, zero padding + frame index in column 0 :158-163) -- for all

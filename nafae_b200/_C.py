@@ -33,6 +33,9 @@ SIGNATURES = {
     "nafae_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
     "nafae_nms_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                   c_void_p, c_size_t, c_void_p]),
+    "nafae_proposal_front_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "nafae_proposal_front": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                     c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nafae_proposal_tail": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "ROIAlignForwardLaucher": (c_int, [c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -34,6 +34,37 @@ def proposal_tail(proposals, scores, pre_nms_topN, post_nms_topN, nms_thresh, re
     return (rois, rsc, num) if return_num else (rois, rsc)
 
 
+def proposal_front(rpn_cls_prob, rpn_bbox_pred, im_info, anchors, feat_stride, pre_nms_topN, return_order=False):
+    """Everything `_ProposalLayer.forward` does before its per-frame loop (proposal_layer.py:66-125) in
+    two launches: anchors + bbox_transform_inv + clip_boxes + per-frame descending score sort.
+    rpn_cls_prob (B, 2A, H, W), rpn_bbox_pred (B, 4A, H, W): CUDA f32; im_info (B, 3); anchors (A, 4).
+    Returns (proposals (B, m, 4), scores (B, m)[, order (B, m) int32]) sorted by score, ready for
+    `proposal_tail`."""
+    cls = _C.f32c(rpn_cls_prob, "rpn_cls_prob")
+    dl = _C.f32c(rpn_bbox_pred, "rpn_bbox_pred")
+    dev = cls.device
+    B, A2, H, W = cls.shape
+    A = A2 // 2
+    if dl.shape != (B, 4 * A, H, W):
+        raise ValueError("rpn_bbox_pred must be (B, 4A, H, W) matching rpn_cls_prob (B, 2A, H, W)")
+    info = torch.as_tensor(im_info, dtype=torch.float32).to(dev).contiguous().view(B, -1)
+    anc = torch.as_tensor(anchors, dtype=torch.float32).to(dev).contiguous()
+    n = H * W * A
+    pre = int(pre_nms_topN)
+    m = pre if (0 < pre < B * n and pre < n) else n
+    props = torch.empty((B, m, 4), dtype=torch.float32, device=dev)
+    scrs = torch.empty((B, m), dtype=torch.float32, device=dev)
+    order = torch.empty((B, m), dtype=torch.int32, device=dev) if return_order else None
+    nbytes = int(_C.lib.nafae_proposal_front_workspace_bytes(B, A, H, W))
+    ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _C.lib.nafae_proposal_front(_C.ptr(cls), _C.ptr(dl), _C.ptr(info), _C.ptr(anc), B, A, H, W,
+                                         float(feat_stride), pre, _C.ptr(props), _C.ptr(scrs), _C.ptr(order),
+                                         _C.ptr(ws), nbytes, _C.stream(dev))
+    _C.check(st, "nafae_proposal_front")
+    return (props, scrs, order) if return_order else (props, scrs)
+
+
 class _ProposalLayer(torch.nn.Module):
     """Mirror of the reference `_ProposalLayer` (lib/model/rpn/proposal_layer.py:26-165): anchors +
     deltas -> boxes -> clip -> per-frame score sort -> NMS -> top-N -> zero-padded `(B, N, 5)` rois.
@@ -41,8 +72,9 @@ class _ProposalLayer(torch.nn.Module):
     Same constructor (`feat_stride, scales, ratios`) and `forward(input)` with
     `input = (rpn_cls_prob, rpn_bbox_pred, im_info, cfg_key)`; the TEST/TRAIN thresholds come from a
     `cfg`-like object (`cfg[cfg_key].RPN_PRE_NMS_TOP_N` ...) passed at construction instead of the
-    reference's module-global.  Everything up to the sort is the reference's own torch arithmetic
-    (:80-125); the Python loop over frames (:130-163) is one `proposal_tail` launch.
+    reference's module-global.  The whole forward is three kernel launches: `proposal_front`
+    (decode + clip, then the per-frame sort) and `proposal_tail` (NMS + top-N + padding for all
+    frames); no per-frame Python loop, no eager tensor arithmetic, no host synchronisation.
     """
 
     def __init__(self, feat_stride, scales, ratios, cfg):
@@ -57,29 +89,13 @@ class _ProposalLayer(torch.nn.Module):
         self.roi_scores = None
 
     def forward(self, input):
-        from .bbox_transform import bbox_transform_inv, clip_boxes
-        scores = input[0][:, self._num_anchors:, :, :]  # fg probabilities
-        bbox_deltas, im_info, cfg_key = input[1], input[2], input[3]
+        rpn_cls_prob, bbox_deltas, im_info, cfg_key = input[0], input[1], input[2], input[3]
         c = getattr(self._cfg, cfg_key) if not isinstance(self._cfg, dict) else self._cfg[cfg_key]
         pre_nms_topN, post_nms_topN, nms_thresh = c.RPN_PRE_NMS_TOP_N, c.RPN_POST_NMS_TOP_N, c.RPN_NMS_THRESH
-        batch_size = bbox_deltas.size(0)
-        H, W = scores.size(2), scores.size(3)
-        dev = scores.device
-        sx = torch.arange(0, W, device=dev, dtype=torch.float32) * self._feat_stride
-        sy = torch.arange(0, H, device=dev, dtype=torch.float32) * self._feat_stride
-        yy, xx = torch.meshgrid(sy, sx, indexing="ij")
-        shifts = torch.stack((xx.reshape(-1), yy.reshape(-1), xx.reshape(-1), yy.reshape(-1)), 1)
-        A, K = self._num_anchors, shifts.size(0)
-        anchors = (self._anchors.to(dev).view(1, A, 4) + shifts.view(K, 1, 4)).view(1, K * A, 4)
-        anchors = anchors.expand(batch_size, K * A, 4)
-        bbox_deltas = bbox_deltas.permute(0, 2, 3, 1).contiguous().view(batch_size, -1, 4)
-        scores = scores.permute(0, 2, 3, 1).contiguous().view(batch_size, -1)
-        proposals = clip_boxes(bbox_transform_inv(anchors, bbox_deltas, batch_size), im_info, batch_size)
-        _, order = torch.sort(scores, 1, True)  # :125
-        if 0 < pre_nms_topN < scores.numel():   # :139-140 (numel of the whole batch, as there)
-            order = order[:, :pre_nms_topN]
-        props = proposals.gather(1, order.unsqueeze(2).expand(-1, -1, 4)).contiguous()
-        scrs = scores.gather(1, order).contiguous()
+        if self._anchors.device != rpn_cls_prob.device:
+            self._anchors = self._anchors.to(rpn_cls_prob.device)
+        props, scrs = proposal_front(rpn_cls_prob, bbox_deltas, im_info, self._anchors, self._feat_stride,
+                                     pre_nms_topN)
         output, self.roi_scores = proposal_tail(props, scrs, 0, post_nms_topN, nms_thresh)
         return output
 
