@@ -44,6 +44,9 @@ typedef struct CUstream_st* cudaStream_t; /* same opaque handle as CUDA driver_t
 #define NAFAE_FLAG_OUT_BF16 4u /* nafae_roi_align_forward: top_data is bf16 -- the (R, C*7*7) row-major
                                   A operand of the bridge GEMM (nafae_gemm_bf16_tn) written directly,
                                   half the output bytes; bandwidth-kernel shapes only */
+#define NAFAE_FLAG_OVERWRITE 8u /* nafae_roi_align_backward: bottom_diff is OVERWRITTEN (it need not be
+                                   zero-filled).  RoIAlignAvg 7x7 then runs the atomic-free cell-gather
+                                   kernel: every cell written once, deterministic */
 #define NAFAE_FLAG_EXACT 1u /* reference-order arithmetic (mixed fp32/fp64 exactly as the
                                reference kernel evaluates it): bit-identical pooled features,
                                slower.  Default (0) = fp32 FMA path, <= 1e-4 relative. */
@@ -176,7 +179,10 @@ int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int b
 /* Backward of the fused operator (roi_align_backward_cuda, src/roi_align_cuda.h:4-5, preceded by
  * the pool's backward that autograd derives).  top_diff (R, C, out_height, out_width);
  * bottom_data is only read for NAFAE_POOL_MAX (may be NULL otherwise).  ACCUMULATES into
- * bottom_diff (B, C, H, W), which the caller zero-fills. */
+ * bottom_diff (B, C, H, W), which the caller zero-fills (functions/roi_align.py:38-39) -- unless
+ * NAFAE_FLAG_OVERWRITE is set: then bottom_diff is fully written by the call (no zero-fill needed),
+ * and the RoIAlignAvg 7x7 case uses a kernel without atomics in which a CTA owns a (frame, 8-channel)
+ * slab of bottom_diff and every thread gathers its own cells (fixed summation order). */
 int nafae_roi_align_backward(const float* top_diff, const float* bottom_data, float spatial_scale,
                              int batch_size, int num_rois, int height, int width, int channels,
                              int out_height, int out_width, int pool_mode, const float* bottom_rois,

@@ -114,6 +114,7 @@ POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 FLAG_EXACT = 1
 FLAG_NO_GATE = 2
 FLAG_OUT_BF16 = 4
+FLAG_OVERWRITE = 8
 GATE_BYTES = 32
 ROI_ALIGN_WS_BYTES = 64
 

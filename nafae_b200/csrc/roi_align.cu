@@ -29,48 +29,10 @@
 
 #include <type_traits>
 
-#include "common.cuh"
+#include "roi_geom.cuh"
 
 namespace nafae {
 namespace {
-
-// ------------------------------------------------------------------------ geometry ----
-struct RoiGeom {
-  float start_w, start_h, bin_w, bin_h;
-  int batch;
-};
-
-// roi_align_kernel.cu:33-43 as compiled: end-start is fma(x2, s, -RN(x1*s)); "+ 1." in double
-// then fmaxf's float conversion is an exact float add; bin is a double division rounded to float.
-__device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ roi, float scale, int sh,
-                                            int sw) {
-  RoiGeom g;
-  g.batch = (int)roi[0];
-  g.start_w = __fmul_rn(roi[1], scale);
-  g.start_h = __fmul_rn(roi[2], scale);
-  const float rw = fmaxf(__fadd_rn(__fmaf_rn(roi[3], scale, -g.start_w), 1.f), 0.f);
-  const float rh = fmaxf(__fadd_rn(__fmaf_rn(roi[4], scale, -g.start_h), 1.f), 0.f);
-  g.bin_h = __double2float_rn(__ddiv_rn((double)rh, __dsub_rn((double)sh, 1.)));
-  g.bin_w = __double2float_rn(__ddiv_rn((double)rw, __dsub_rn((double)sw, 1.)));
-  return g;
-}
-
-// one axis of a sample point (roi_align_kernel.cu:45-49,54,58-59): returns false if outside
-__device__ __forceinline__ bool axis_sample(float start, float bin, int p, int extent, int* cell,
-                                            float* ratio) {
-  const float x = __fmaf_rn((float)p, bin, start);
-  if (x < 0.f || x >= (float)extent || x != x) {
-    *cell = 0;
-    *ratio = 0.f;
-    // NaN: the reference's comparisons are all false -> it would read out of bounds; we
-    // define the sample as outside instead.
-    return false;
-  }
-  const int c = (int)fminf(floorf(x), (float)(extent - 2));
-  *cell = c;
-  *ratio = __fsub_rn(x, (float)c);
-  return true;
-}
 
 // roi_align_kernel.cu:64-67 as compiled (see header comment)
 __device__ __forceinline__ float interp_exact(float ul, float ur, float dl, float dr, float hr,
@@ -742,6 +704,12 @@ int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W
   return launch_slab<0, 0, 2, 0>(p, pool, bf16, smem, stream);
 }
 
+}  // namespace
+// roi_align_bwd.cu: cell-gather backward without atomics (1 launched, 0 not eligible, < 0 error)
+int try_launch_avg_bwd_gather(const float* top_diff, float scale, int B, int R, int H, int W, int C,
+                              const float* rois, float* bottom_diff, cudaStream_t stream);
+namespace {
+
 int grid_for(long long total) {
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
@@ -827,6 +795,22 @@ NAFAE_API int nafae_roi_align_backward(const float* top_diff, const float* botto
                 "roi_align backward: max pooling needs bottom_data");
   const int sh = pool_mode ? out_height + 1 : out_height, sw = pool_mode ? out_width + 1 : out_width;
   const long long total = (long long)num_rois * channels * sh * sw;
+  const bool overwrite = (flags & NAFAE_FLAG_OVERWRITE) != 0;
+  if (overwrite && batch_size > 0 && channels > 0) {
+    NAFAE_REQUIRE(bottom_diff && height >= 1 && width >= 1, "roi_align backward: NULL / empty bottom_diff");
+    if (total > 0 && !(flags & NAFAE_FLAG_EXACT) && pool_mode == NAFAE_POOL_AVG && out_height == kOut &&
+        out_width == kOut && top_diff && bottom_rois) {
+      const int st = try_launch_avg_bwd_gather(top_diff, spatial_scale, batch_size, num_rois, height, width,
+                                               channels, bottom_rois, bottom_diff, stream);
+      if (st != 0) return st;
+    }
+    cudaError_t e = cudaMemsetAsync(bottom_diff, 0, sizeof(float) * (size_t)batch_size * channels * height * width,
+                                    stream);
+    if (e != cudaSuccess) {
+      set_error("roi_align backward: cudaMemsetAsync: %s", cudaGetErrorString(e));
+      return -(int)e;
+    }
+  }
   if (total == 0 || batch_size == 0) return 1;
   NAFAE_REQUIRE(height >= 2 && width >= 2, "roi_align: feature map must be at least 2x2");
   NAFAE_REQUIRE(top_diff && bottom_rois && bottom_diff, "roi_align: NULL buffer");

@@ -1,0 +1,254 @@
+// RoIAlignAvg backward WITHOUT atomics (sm_100a): cell-gather with exclusive ownership.
+//
+// Reference: ROIAlignBackward (lib/model/roi_align/src/roi_align_kernel.cu:94-143) scatters every
+// sample's gradient to four cells with atomicAdd into a pre-zeroed (B, C, H, W) tensor, preceded by
+// avg_pool2d's backward (autograd); at cfg2 that is 26 M float atomics and a 156 MB memset.
+// Here a CTA owns one (frame, 8-channel) slab of bottom_diff outright: every thread owns a few
+// CELLS of that slab for all 8 channels and GATHERS what the frame's RoIs send there, so the output
+// is written exactly once, coalesced, with plain stores -- no atomics, no zero-fill, a fixed summation
+// order (deterministic).  Which samples of a RoI reach a cell is separable: sample row ph reaches cell
+// row y with weight (1 - h_ratio) when hstart[ph] == y and h_ratio when hstart[ph] == y - 1 (ranges
+// of ph, monotone), likewise for columns; two byte-tables per RoI (rows, columns) make the test two
+// shared-memory reads, and most (RoI, cell) pairs are rejected by them.
+// The pool's backward is folded in: sample gradient gs[ph][pw] = sum of the <= 4 output gradients
+// whose 2x2 window contains the sample, the 1/4 sits in the column weights.
+//
+// 7x7 outputs of an 8x8 sample grid with average pooling only (RoIAlignAvg(7, 7, s), the one
+// configuration the reference instantiates); everything else takes the generic atomic kernel.
+#include "roi_geom.cuh"
+
+namespace nafae {
+namespace {
+
+constexpr int kS = 8, kOut = 7;
+constexpr int kBwCg = 8;          // channels per CTA
+constexpr int kBwThreads = 512;
+constexpr int kBwWarps = kBwThreads / 32;
+constexpr int kBwChunk = 16;      // RoIs whose tables / gradients are resident at a time
+constexpr int kBwCells = 4;       // cells per thread  => H*W <= 2048
+constexpr int kBwMaxDim = 128;    // H, W <= 128
+
+struct BwAxis {  // per RoI
+  int hcell[kS];   // cell row of sample row ph (hstart), -1000 when the sample row is outside
+  float h0[kS], h1[kS];
+  int wcell[kS];
+  float w0[kS], w1[kS];  // * 1/4 (average pool)
+};
+
+struct BwParams {
+  const float* top_diff;   // (R, C, 7, 7)
+  const float* rois;       // (R, 5)
+  float* bottom_diff;      // (B, C, H, W), fully overwritten
+  float scale;
+  int B, R, H, W, C;
+};
+
+__global__ void __launch_bounds__(kBwThreads, 1) align_avg_bwd_gather(const BwParams p) {
+  extern __shared__ __align__(16) unsigned char bw_smem[];
+  float* gs = reinterpret_cast<float*>(bw_smem);                       // [chunk][64 samples][8 ch]
+  float* gst = gs + kBwChunk * 64 * kBwCg;                             // [chunk][8 ch][49]
+  BwAxis* ax = reinterpret_cast<BwAxis*>(gst + kBwChunk * kBwCg * 49); // [chunk]
+  uchar4* rowmap = reinterpret_cast<uchar4*>(ax + kBwChunk);           // [chunk][H]: lo0, n0, lo1, n1
+  uchar4* colmap = rowmap + kBwChunk * p.H;                            // [chunk][W]
+  __shared__ int s_ids[kBwChunk];
+  __shared__ int s_wcnt[kBwWarps];
+  __shared__ int s_n, s_next;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int groups = p.C / kBwCg;
+  const int f = blockIdx.x / groups, c0 = (blockIdx.x % groups) * kBwCg;
+  const int hw = p.H * p.W;
+
+  float acc[kBwCells][kBwCg];
+#pragma unroll
+  for (int i = 0; i < kBwCells; ++i)
+#pragma unroll
+    for (int c = 0; c < kBwCg; ++c) acc[i][c] = 0.f;
+  int cy[kBwCells], cx[kBwCells];
+#pragma unroll
+  for (int i = 0; i < kBwCells; ++i) {
+    const int cell = tid + i * kBwThreads;
+    cy[i] = cell < hw ? cell / p.W : -1;
+    cx[i] = cell < hw ? cell - (cell / p.W) * p.W : -1;
+  }
+
+  int r_next = 0;
+  while (r_next < p.R) {
+    // ---- next chunk: the first kBwChunk RoIs of frame f at or after r_next, in index order
+    if (tid == 0) {
+      s_n = 0;
+      s_next = p.R;
+    }
+    __syncthreads();
+    for (int base = r_next; base < p.R; base += kBwThreads) {
+      const int r = base + tid;
+      const bool hit = r < p.R && (int)__ldg(p.rois + (size_t)r * 5) == f;
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) s_wcnt[warp] = __popc(bal);
+      __syncthreads();
+      const int have = s_n;
+      int before = have, tot = 0;
+      for (int w = 0; w < kBwWarps; ++w) {
+        const int cw = s_wcnt[w];
+        if (w < warp) before += cw;
+        tot += cw;
+      }
+      const int pos = before + __popc(bal & ((1u << lane) - 1u));
+      if (hit && pos < kBwChunk) s_ids[pos] = r;
+      if (hit && pos == kBwChunk) s_next = r;  // first RoI that did not fit (unique thread)
+      __syncthreads();
+      if (have + tot > kBwChunk) {
+        if (tid == 0) s_n = kBwChunk;
+        break;
+      }
+      if (tid == 0) {
+        s_n = have + tot;
+        if (have + tot == kBwChunk) s_next = min(base + kBwThreads, p.R);
+      }
+      if (have + tot == kBwChunk) break;
+    }
+    __syncthreads();
+    const int n = s_n;
+    r_next = s_next;
+    if (n == 0) break;
+
+    // ---- per-RoI axis tables: one thread per (RoI, axis)
+    if (tid < 2 * n) {
+      const int j = tid >> 1;
+      const bool is_w = tid & 1;
+      const float* roi = p.rois + (size_t)s_ids[j] * 5;
+      const float lo = __ldg(roi + (is_w ? 1 : 2)), hi = __ldg(roi + (is_w ? 3 : 4));
+      const float start = __fmul_rn(lo, p.scale);
+      const float ext = fmaxf(__fadd_rn(__fmaf_rn(hi, p.scale, -start), 1.f), 0.f);
+      const float bin = __double2float_rn(__ddiv_rn((double)ext, __dsub_rn((double)kS, 1.)));
+#pragma unroll
+      for (int k = 0; k < kS; ++k) {
+        int cell;
+        float ratio;
+        const bool ok = axis_sample(start, bin, k, is_w ? p.W : p.H, &cell, &ratio);
+        if (is_w) {
+          ax[j].wcell[k] = ok ? cell : -1000;
+          ax[j].w0[k] = ok ? 0.25f * (1.f - ratio) : 0.f;
+          ax[j].w1[k] = ok ? 0.25f * ratio : 0.f;
+        } else {
+          ax[j].hcell[k] = ok ? cell : -1000;
+          ax[j].h0[k] = ok ? 1.f - ratio : 0.f;
+          ax[j].h1[k] = ok ? ratio : 0.f;
+        }
+      }
+    }
+    // ---- output gradients of the chunk -> shared (coalesced: 8 channels x 49 are contiguous per RoI)
+    for (int i = tid; i < n * kBwCg * 49; i += kBwThreads) {
+      const int j = i / (kBwCg * 49), rem = i - j * (kBwCg * 49);
+      gst[i] = __ldg(p.top_diff + ((size_t)s_ids[j] * p.C + c0) * 49 + rem);
+    }
+    __syncthreads();
+    // ---- row / column maps: which sample rows reach cell row y with weight h0 (hstart == y) / h1
+    for (int i = tid; i < n * (p.H + p.W); i += kBwThreads) {
+      const int j = i / (p.H + p.W), k = i - j * (p.H + p.W);
+      const bool is_w = k >= p.H;
+      const int v = is_w ? k - p.H : k;
+      const int* cells = is_w ? ax[j].wcell : ax[j].hcell;
+      int lo0 = 0, n0 = 0, lo1 = 0, n1 = 0;
+#pragma unroll
+      for (int s = 0; s < kS; ++s) {
+        const int cc = cells[s];
+        if (cc == v) {
+          if (n0 == 0) lo0 = s;
+          ++n0;
+        }
+        if (cc == v - 1) {
+          if (n1 == 0) lo1 = s;
+          ++n1;
+        }
+      }
+      const uchar4 m = make_uchar4((unsigned char)lo0, (unsigned char)n0, (unsigned char)lo1, (unsigned char)n1);
+      if (is_w) colmap[j * p.W + v] = m;
+      else rowmap[j * p.H + v] = m;
+    }
+    // ---- sample gradients: avg_pool2d(2, 1) backward, layout [RoI][sample][channel]
+    for (int i = tid; i < n * 64 * kBwCg; i += kBwThreads) {
+      const int c = i % kBwCg, s = (i / kBwCg) % 64, j = i / (kBwCg * 64);
+      const int ph = s >> 3, pw = s & 7;
+      const float* g = gst + (j * kBwCg + c) * 49;
+      float v = 0.f;
+      if (ph > 0 && pw > 0) v += g[(ph - 1) * kOut + pw - 1];
+      if (ph > 0 && pw < kOut) v += g[(ph - 1) * kOut + pw];
+      if (ph < kOut && pw > 0) v += g[ph * kOut + pw - 1];
+      if (ph < kOut && pw < kOut) v += g[ph * kOut + pw];
+      gs[i] = v;
+    }
+    __syncthreads();
+    // ---- gather: every owned cell collects from every RoI of the chunk
+#pragma unroll
+    for (int i = 0; i < kBwCells; ++i) {
+      if (cy[i] < 0) continue;
+      for (int j = 0; j < n; ++j) {
+        const uchar4 rm = rowmap[j * p.H + cy[i]];
+        if (rm.y + rm.w == 0) continue;
+        const uchar4 cm = colmap[j * p.W + cx[i]];
+        if (cm.y + cm.w == 0) continue;
+        const BwAxis& a = ax[j];
+        for (int rr = 0; rr < rm.y + rm.w; ++rr) {
+          const int ph = rr < rm.y ? rm.x + rr : rm.z + (rr - rm.y);
+          const float wy = rr < rm.y ? a.h0[ph] : a.h1[ph];
+          for (int qq = 0; qq < cm.y + cm.w; ++qq) {
+            const int pw = qq < cm.y ? cm.x + qq : cm.z + (qq - cm.y);
+            const float wgt = wy * (qq < cm.y ? a.w0[pw] : a.w1[pw]);
+            const float4* g4 = reinterpret_cast<const float4*>(gs + ((size_t)j * 64 + ph * 8 + pw) * kBwCg);
+            const float4 ga = g4[0], gb = g4[1];
+            acc[i][0] = fmaf(wgt, ga.x, acc[i][0]);
+            acc[i][1] = fmaf(wgt, ga.y, acc[i][1]);
+            acc[i][2] = fmaf(wgt, ga.z, acc[i][2]);
+            acc[i][3] = fmaf(wgt, ga.w, acc[i][3]);
+            acc[i][4] = fmaf(wgt, gb.x, acc[i][4]);
+            acc[i][5] = fmaf(wgt, gb.y, acc[i][5]);
+            acc[i][6] = fmaf(wgt, gb.z, acc[i][6]);
+            acc[i][7] = fmaf(wgt, gb.w, acc[i][7]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // the next chunk rewrites the shared tables
+  }
+  // ---- every cell of the slab is written exactly once (frames without RoIs: zeros)
+#pragma unroll
+  for (int i = 0; i < kBwCells; ++i) {
+    const int cell = tid + i * kBwThreads;
+    if (cell < hw) {
+#pragma unroll
+      for (int c = 0; c < kBwCg; ++c)
+        p.bottom_diff[((size_t)f * p.C + c0 + c) * hw + cell] = acc[i][c];
+    }
+  }
+}
+
+}  // namespace
+
+// 1 launched, 0 not eligible (caller uses the generic kernel), < 0 launch error
+int try_launch_avg_bwd_gather(const float* top_diff, float scale, int B, int R, int H, int W, int C,
+                              const float* rois, float* bottom_diff, cudaStream_t stream) {
+  if (C % kBwCg != 0 || H < 2 || W < 2 || H > kBwMaxDim || W > kBwMaxDim || H * W > kBwCells * kBwThreads) return 0;
+  if ((long long)B * (C / kBwCg) > 0x7fffffffLL) return 0;
+  const size_t smem = (size_t)kBwChunk * 64 * kBwCg * 4 + (size_t)kBwChunk * kBwCg * 49 * 4 +
+                      sizeof(BwAxis) * kBwChunk + sizeof(uchar4) * kBwChunk * (size_t)(H + W);
+  cudaError_t e = cudaFuncSetAttribute(align_avg_bwd_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("roi_align backward: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+    return -(int)e;
+  }
+  BwParams p;
+  p.top_diff = top_diff;
+  p.rois = rois;
+  p.bottom_diff = bottom_diff;
+  p.scale = scale;
+  p.B = B;
+  p.R = R;
+  p.H = H;
+  p.W = W;
+  p.C = C;
+  align_avg_bwd_gather<<<B * (C / kBwCg), kBwThreads, smem, stream>>>(p);
+  return launch_status("align_avg_bwd_gather");
+}
+
+}  // namespace nafae

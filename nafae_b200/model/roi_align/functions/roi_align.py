@@ -48,12 +48,14 @@ class _RoIAlign(torch.autograd.Function):
         rois = saved[0]
         features = saved[1] if pool_mode == _C.POOL_MAX else None
         grad_output = _C.f32c(grad_output, "grad_output")
-        # the kernels accumulate: zero-filled by the caller like functions/roi_align.py:38-39
-        grad_input = torch.zeros((B, C, H, W), dtype=torch.float32, device=grad_output.device)
+        # the reference zero-fills and accumulates with atomics (functions/roi_align.py:38-39); here the
+        # call overwrites grad_input (NAFAE_FLAG_OVERWRITE): no memset, and RoIAlignAvg 7x7 takes the
+        # atomic-free cell-gather kernel
+        grad_input = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_output.device)
         with torch.cuda.device(grad_output.device):
             st = _C.lib.nafae_roi_align_backward(
                 _C.ptr(grad_output), _C.ptr(features), scale, B, rois.size(0), H, W, C, out_h,
-                out_w, pool_mode, _C.ptr(rois), _C.ptr(grad_input), flags,
+                out_w, pool_mode, _C.ptr(rois), _C.ptr(grad_input), flags | _C.FLAG_OVERWRITE,
                 _C.stream(grad_output.device))
         _C.check(st, "nafae_roi_align_backward")
         return grad_input, None, None, None, None, None, None  # (grad, None) as ref :47

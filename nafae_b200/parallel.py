@@ -18,6 +18,10 @@ import torch.distributed as dist
 COMM_SMS = int(os.environ.get("NAFAE_COMM_SMS", "16"))
 
 
+# largest world size for which make_allreduce("auto") prefers the peer-memory kernel over NVLS
+AUTO_PEER_MAX_WORLD = int(os.environ.get("NAFAE_AUTO_PEER_MAX_WORLD", "2"))
+
+
 def trainable_grad_elems(vis_fc_dim=4096, glove_dim=200, ebd_dim=512):
     return (ebd_dim * vis_fc_dim + ebd_dim) + (ebd_dim * glove_dim + ebd_dim) + 2 * ebd_dim
 
@@ -362,6 +366,10 @@ def make_allreduce(numel, device, kind="auto", peer_kw=None, mc_kw=None):
     memory).  `kind` = "auto" | "multicast" | "peer"; all ranks take the same decision."""
     if kind not in ("auto", "multicast", "peer"):
         raise ValueError("kind must be auto, multicast or peer")
+    if kind == "auto" and dist.get_world_size() <= AUTO_PEER_MAX_WORLD:
+        # measured (profiles/RESULTS.md): with two ranks the in-switch reduction moves MORE bytes over
+        # NVLink than the peer pull / push (every rank's copy travels to the switch), 73 vs 69 us / step
+        kind = "peer"
     if kind != "peer":
         mine = multicast_supported(device)
         flags = [None] * dist.get_world_size()

@@ -121,8 +121,9 @@ if HAVE_MC:
         check_allreduce("multicast (NVLS) %dx%d" % (ctas, thr),
                         parallel.MulticastAllReduce(N, dev, num_ctas=ctas, cta_threads=thr))
     ar = parallel.make_allreduce(N, dev)
-    if ar.kind != "multicast":
-        failures.append("make_allreduce(auto) did not pick the multicast kernel")
+    want_kind = "peer" if world <= parallel.AUTO_PEER_MAX_WORLD else "multicast"
+    if ar.kind != want_kind:
+        failures.append("make_allreduce(auto) picked %s, expected %s at world %d" % (ar.kind, want_kind, world))
     ar.close()
 else:
     ar = parallel.make_allreduce(N, dev)
