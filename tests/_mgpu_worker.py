@@ -139,52 +139,62 @@ from oracle import dvsa as odvsa  # noqa: E402  (checker)
 c = dict(synth.CONFIGS["cfg2"])
 c.update(C=32, n=600)  # small maps / fewer proposals: the DVSA half is the full cfg2 shape
 host = [synth.make_batch(c, 500 + 10 * rank + i) for i in range(2)]
-steps = [GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], c["C"], c["H"], c["W"], c["n"],
-                       pre_nms_topn=c["pre"], Delta=c["Delta"], vis_lam=c["vis_lam"], train=True,
-                       device=dev) for _ in range(2)]
-buckets = [parallel.make_allreduce(N, dev) for _ in range(2)]
-for st, b, hb in zip(steps, buckets, host):
-    st.grad_word = b.views([(st.NQ, c["D"])])[0]
-    st.load(hb)
-    st.run()
-prev = _C.lib.nafae_set_reserved_sms(32)
-side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-comm = torch.cuda.Stream(dev)
-torch.cuda.synchronize()
-graphs = []
-for j in range(2):
-    def ar_branch(cur, j=j):
-        comm.wait_stream(cur)
-        with torch.cuda.stream(comm):
-            steps[j].wait_gate(1)
-            buckets[j].launch()
-        return comm
-    graphs.append(capture_pipelined(steps[j], steps[1 - j], side, ar_branch))
-torch.cuda.synchronize()
-dist.barrier()
 want = []
 for hb in host:
     ref = odvsa.dvsa_forward_backward(hb["vis_feats"], hb["word_feats"], hb["lens"], c["Na"], c["Nb"],
                                       c["Ne"], c["Delta"], c["vis_lam"], "train")
     mine = torch.from_numpy(np.ascontiguousarray(ref["grad_word"])).to(dev)
     want.append(gather_all(mine).double().mean(0))
-for k in range(6):
-    graphs[k & 1].replay()
-    # replay k: head of set 1-k&1 wrote bucket[1-k&1]; the all-reduce averaged bucket[k&1] (filled by
-    # the previous replay's head, or by the warm-up run for k = 0)
+
+
+def run_dp(kind):
+    steps = [GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], c["C"], c["H"], c["W"], c["n"],
+                           pre_nms_topn=c["pre"], Delta=c["Delta"], vis_lam=c["vis_lam"], train=True,
+                           device=dev) for _ in range(2)]
+    buckets = [parallel.make_allreduce(N, dev, kind=kind) for _ in range(2)]
+    for st, b, hb in zip(steps, buckets, host):
+        st.grad_word = b.views([(st.NQ, c["D"])])[0]
+        st.load(hb)
+        st.run()
+    prev = _C.lib.nafae_set_reserved_sms(32)
+    side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    comm = torch.cuda.Stream(dev)
     torch.cuda.synchronize()
-    j = k & 1
-    got = steps[j].grad_word.double()
-    scale = want[j].abs().max()
-    err = ((got - want[j]).abs().max() / scale).item()
-    allr = gather_all(steps[j].grad_word.reshape(-1))
-    same = bool((allr.view(torch.int32) == allr[0].view(torch.int32)).all().item())
-    if not (err < 1e-4 and same):
-        failures.append("pipelined DP step %d: grad_word rel err %.3e, replicas identical %s" % (k, err, same))
-log("pipelined DP steps (%s all-reduce, gated): %s" % (buckets[0].kind, "ok" if not failures else failures[-1]))
-_C.lib.nafae_set_reserved_sms(prev)
-for b in buckets:
-    b.close()
+    graphs = []
+    for j in range(2):
+        def ar_branch(cur, j=j):
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                steps[j].wait_gate(1)
+                buckets[j].launch()
+            return comm
+        graphs.append(capture_pipelined(steps[j], steps[1 - j], side, ar_branch))
+    torch.cuda.synchronize()
+    dist.barrier()
+    bad = 0
+    for k in range(6):
+        graphs[k & 1].replay()
+        # replay k: head of set 1-k&1 wrote bucket[1-k&1]; the all-reduce averaged bucket[k&1] (filled by
+        # the previous replay's head, or by the warm-up run for k = 0)
+        torch.cuda.synchronize()
+        j = k & 1
+        got = steps[j].grad_word.double()
+        err = ((got - want[j]).abs().max() / want[j].abs().max()).item()
+        allr = gather_all(steps[j].grad_word.reshape(-1))
+        same = bool((allr.view(torch.int32) == allr[0].view(torch.int32)).all().item())
+        if not (err < 1e-4 and same):
+            bad += 1
+            failures.append("pipelined DP step %d (%s): grad_word rel err %.3e, replicas identical %s"
+                            % (k, buckets[0].kind, err, same))
+    log("pipelined DP steps (%s all-reduce, gated): %s" % (buckets[0].kind, "ok" if not bad else "FAILED"))
+    _C.lib.nafae_set_reserved_sms(prev)
+    for b in buckets:
+        b.close()
+    del graphs
+
+
+for kind in (("peer", "multicast") if HAVE_MC else ("peer",)):
+    run_dp(kind)
 
 # ------------------------------------------------------------- 3. HeadTrainer steps ----
 from nafae_b200.bridge import VisEbd, WordEbd  # noqa: E402
