@@ -21,12 +21,13 @@ namespace nafae {
 namespace {
 
 constexpr int kS = 8, kOut = 7;
-constexpr int kBwCg = 8;          // channels per CTA
+constexpr int kBwCg = 8;          // channels per pass
 constexpr int kBwThreads = 512;
 constexpr int kBwWarps = kBwThreads / 32;
-constexpr int kBwChunk = 16;      // RoIs whose tables / gradients are resident at a time
+constexpr int kBwChunk = 24;      // RoIs whose tables / gradients are resident at a time
 constexpr int kBwCells = 4;       // cells per thread  => H*W <= 2048
 constexpr int kBwMaxDim = 128;    // H, W <= 128
+constexpr int kBwGroups = 4;      // channel groups (of kBwCg) a CTA works through with one set of tables
 
 struct BwAxis {  // per RoI
   int hcell[kS];   // cell row of sample row ph (hstart), -1000 when the sample row is outside
@@ -41,9 +42,12 @@ struct BwParams {
   float* bottom_diff;      // (B, C, H, W), fully overwritten
   float scale;
   int B, R, H, W, C;
+  int splits;              // CTAs per frame; each takes C / splits channels in groups of kBwCg
 };
 
-__global__ void __launch_bounds__(kBwThreads, 1) align_avg_bwd_gather(const BwParams p) {
+// Two CTAs per SM (<= 64 registers, ~85 KB of shared memory each): one CTA's global round trips
+// (RoI scan, gradient staging) hide behind the other's gather.
+__global__ void __launch_bounds__(kBwThreads, 2) align_avg_bwd_gather(const BwParams p) {
   extern __shared__ __align__(16) unsigned char bw_smem[];
   float* gs = reinterpret_cast<float*>(bw_smem);                       // [chunk][64 samples][8 ch]
   float* gst = gs + kBwChunk * 64 * kBwCg;                             // [chunk][8 ch][49]
@@ -55,15 +59,12 @@ __global__ void __launch_bounds__(kBwThreads, 1) align_avg_bwd_gather(const BwPa
   __shared__ int s_n, s_next;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int groups = p.C / kBwCg;
-  const int f = blockIdx.x / groups, c0 = (blockIdx.x % groups) * kBwCg;
+  const int f = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+  const int ch_per_split = p.C / p.splits;
+  const int ch_begin = split * ch_per_split;
+  const int ngroups = ch_per_split / kBwCg;
   const int hw = p.H * p.W;
 
-  float acc[kBwCells][kBwCg];
-#pragma unroll
-  for (int i = 0; i < kBwCells; ++i)
-#pragma unroll
-    for (int c = 0; c < kBwCg; ++c) acc[i][c] = 0.f;
   int cy[kBwCells], cx[kBwCells];
 #pragma unroll
   for (int i = 0; i < kBwCells; ++i) {
@@ -73,7 +74,8 @@ __global__ void __launch_bounds__(kBwThreads, 1) align_avg_bwd_gather(const BwPa
   }
 
   int r_next = 0;
-  while (r_next < p.R) {
+  bool first_chunk = true;
+  for (;;) {
     // ---- next chunk: the first kBwChunk RoIs of frame f at or after r_next, in index order
     if (tid == 0) {
       s_n = 0;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) align_avg_bwd_gather(const BwPa
     __syncthreads();
     const int n = s_n;
     r_next = s_next;
-    if (n == 0) break;
+    if (n == 0 && !first_chunk) break;
 
     // ---- per-RoI axis tables: one thread per (RoI, axis)
     if (tid < 2 * n) {
@@ -137,11 +139,6 @@ __global__ void __launch_bounds__(kBwThreads, 1) align_avg_bwd_gather(const BwPa
         }
       }
     }
-    // ---- output gradients of the chunk -> shared (coalesced: 8 channels x 49 are contiguous per RoI)
-    for (int i = tid; i < n * kBwCg * 49; i += kBwThreads) {
-      const int j = i / (kBwCg * 49), rem = i - j * (kBwCg * 49);
-      gst[i] = __ldg(p.top_diff + ((size_t)s_ids[j] * p.C + c0) * 49 + rem);
-    }
     __syncthreads();
     // ---- row / column maps: which sample rows reach cell row y with weight h0 (hstart == y) / h1
     for (int i = tid; i < n * (p.H + p.W); i += kBwThreads) {
@@ -166,60 +163,83 @@ __global__ void __launch_bounds__(kBwThreads, 1) align_avg_bwd_gather(const BwPa
       if (is_w) colmap[j * p.W + v] = m;
       else rowmap[j * p.H + v] = m;
     }
-    // ---- sample gradients: avg_pool2d(2, 1) backward, layout [RoI][sample][channel]
-    for (int i = tid; i < n * 64 * kBwCg; i += kBwThreads) {
-      const int c = i % kBwCg, s = (i / kBwCg) % 64, j = i / (kBwCg * 64);
-      const int ph = s >> 3, pw = s & 7;
-      const float* g = gst + (j * kBwCg + c) * 49;
-      float v = 0.f;
-      if (ph > 0 && pw > 0) v += g[(ph - 1) * kOut + pw - 1];
-      if (ph > 0 && pw < kOut) v += g[(ph - 1) * kOut + pw];
-      if (ph < kOut && pw > 0) v += g[ph * kOut + pw - 1];
-      if (ph < kOut && pw < kOut) v += g[ph * kOut + pw];
-      gs[i] = v;
-    }
-    __syncthreads();
-    // ---- gather: every owned cell collects from every RoI of the chunk
+
+    // ---- the channel groups of this CTA, all with the tables above
+    for (int g = 0; g < ngroups; ++g) {
+      const int c0 = ch_begin + g * kBwCg;
+      __syncthreads();  // previous group's gather is done with gs / gst (and the maps are complete)
+      // output gradients of the chunk -> shared (coalesced: 8 channels x 49 are contiguous per RoI)
+      for (int i = tid; i < n * kBwCg * 49; i += kBwThreads) {
+        const int j = i / (kBwCg * 49), rem = i - j * (kBwCg * 49);
+        gst[i] = __ldg(p.top_diff + ((size_t)s_ids[j] * p.C + c0) * 49 + rem);
+      }
+      // accumulators: zero for the first chunk of the frame, else what the earlier chunks left
+      float acc[kBwCells][kBwCg];
 #pragma unroll
-    for (int i = 0; i < kBwCells; ++i) {
-      if (cy[i] < 0) continue;
-      for (int j = 0; j < n; ++j) {
-        const uchar4 rm = rowmap[j * p.H + cy[i]];
-        if (rm.y + rm.w == 0) continue;
-        const uchar4 cm = colmap[j * p.W + cx[i]];
-        if (cm.y + cm.w == 0) continue;
-        const BwAxis& a = ax[j];
-        for (int rr = 0; rr < rm.y + rm.w; ++rr) {
-          const int ph = rr < rm.y ? rm.x + rr : rm.z + (rr - rm.y);
-          const float wy = rr < rm.y ? a.h0[ph] : a.h1[ph];
-          for (int qq = 0; qq < cm.y + cm.w; ++qq) {
-            const int pw = qq < cm.y ? cm.x + qq : cm.z + (qq - cm.y);
-            const float wgt = wy * (qq < cm.y ? a.w0[pw] : a.w1[pw]);
-            const float4* g4 = reinterpret_cast<const float4*>(gs + ((size_t)j * 64 + ph * 8 + pw) * kBwCg);
-            const float4 ga = g4[0], gb = g4[1];
-            acc[i][0] = fmaf(wgt, ga.x, acc[i][0]);
-            acc[i][1] = fmaf(wgt, ga.y, acc[i][1]);
-            acc[i][2] = fmaf(wgt, ga.z, acc[i][2]);
-            acc[i][3] = fmaf(wgt, ga.w, acc[i][3]);
-            acc[i][4] = fmaf(wgt, gb.x, acc[i][4]);
-            acc[i][5] = fmaf(wgt, gb.y, acc[i][5]);
-            acc[i][6] = fmaf(wgt, gb.z, acc[i][6]);
-            acc[i][7] = fmaf(wgt, gb.w, acc[i][7]);
+      for (int i = 0; i < kBwCells; ++i) {
+        const int cell = tid + i * kBwThreads;
+#pragma unroll
+        for (int c = 0; c < kBwCg; ++c)
+          acc[i][c] = (first_chunk || cell >= hw) ? 0.f : p.bottom_diff[((size_t)f * p.C + c0 + c) * hw + cell];
+      }
+      __syncthreads();
+      // sample gradients: avg_pool2d(2, 1) backward, layout [RoI][sample][channel]
+      for (int i = tid; i < n * 64 * kBwCg; i += kBwThreads) {
+        const int c = i % kBwCg, s = (i / kBwCg) % 64, j = i / (kBwCg * 64);
+        const int ph = s >> 3, pw = s & 7;
+        const float* gg = gst + (j * kBwCg + c) * 49;
+        float v = 0.f;
+        if (ph > 0 && pw > 0) v += gg[(ph - 1) * kOut + pw - 1];
+        if (ph > 0 && pw < kOut) v += gg[(ph - 1) * kOut + pw];
+        if (ph < kOut && pw > 0) v += gg[ph * kOut + pw - 1];
+        if (ph < kOut && pw < kOut) v += gg[ph * kOut + pw];
+        gs[i] = v;
+      }
+      __syncthreads();
+      // gather: every owned cell collects from every RoI of the chunk
+#pragma unroll
+      for (int i = 0; i < kBwCells; ++i) {
+        if (cy[i] < 0) continue;
+        for (int j = 0; j < n; ++j) {
+          const uchar4 rm = rowmap[j * p.H + cy[i]];
+          if (rm.y + rm.w == 0) continue;
+          const uchar4 cm = colmap[j * p.W + cx[i]];
+          if (cm.y + cm.w == 0) continue;
+          const BwAxis& a = ax[j];
+          for (int rr = 0; rr < rm.y + rm.w; ++rr) {
+            const int ph = rr < rm.y ? rm.x + rr : rm.z + (rr - rm.y);
+            const float wy = rr < rm.y ? a.h0[ph] : a.h1[ph];
+            for (int qq = 0; qq < cm.y + cm.w; ++qq) {
+              const int pw = qq < cm.y ? cm.x + qq : cm.z + (qq - cm.y);
+              const float wgt = wy * (qq < cm.y ? a.w0[pw] : a.w1[pw]);
+              const float4* g4 = reinterpret_cast<const float4*>(gs + ((size_t)j * 64 + ph * 8 + pw) * kBwCg);
+              const float4 ga = g4[0], gb = g4[1];
+              acc[i][0] = fmaf(wgt, ga.x, acc[i][0]);
+              acc[i][1] = fmaf(wgt, ga.y, acc[i][1]);
+              acc[i][2] = fmaf(wgt, ga.z, acc[i][2]);
+              acc[i][3] = fmaf(wgt, ga.w, acc[i][3]);
+              acc[i][4] = fmaf(wgt, gb.x, acc[i][4]);
+              acc[i][5] = fmaf(wgt, gb.y, acc[i][5]);
+              acc[i][6] = fmaf(wgt, gb.z, acc[i][6]);
+              acc[i][7] = fmaf(wgt, gb.w, acc[i][7]);
+            }
           }
         }
       }
+      // every cell of the slab is written by its owner only (frames without RoIs: zeros)
+#pragma unroll
+      for (int i = 0; i < kBwCells; ++i) {
+        const int cell = tid + i * kBwThreads;
+        if (cell < hw) {
+#pragma unroll
+          for (int c = 0; c < kBwCg; ++c)
+            p.bottom_diff[((size_t)f * p.C + c0 + c) * hw + cell] = acc[i][c];
+        }
+      }
     }
+    first_chunk = false;
+    if (r_next >= p.R) break;
     __syncthreads();  // the next chunk rewrites the shared tables
-  }
-  // ---- every cell of the slab is written exactly once (frames without RoIs: zeros)
-#pragma unroll
-  for (int i = 0; i < kBwCells; ++i) {
-    const int cell = tid + i * kBwThreads;
-    if (cell < hw) {
-#pragma unroll
-      for (int c = 0; c < kBwCg; ++c)
-        p.bottom_diff[((size_t)f * p.C + c0 + c) * hw + cell] = acc[i][c];
-    }
   }
 }
 
@@ -247,7 +267,11 @@ int try_launch_avg_bwd_gather(const float* top_diff, float scale, int B, int R, 
   p.H = H;
   p.W = W;
   p.C = C;
-  align_avg_bwd_gather<<<B * (C / kBwCg), kBwThreads, smem, stream>>>(p);
+  // CTAs per frame: each works through kBwGroups channel groups with one set of tables (fewer when C is small)
+  int per_cta = kBwGroups * kBwCg;
+  while (per_cta > kBwCg && C % per_cta != 0) per_cta -= kBwCg;
+  p.splits = C / per_cta;
+  align_avg_bwd_gather<<<B * p.splits, kBwThreads, smem, stream>>>(p);
   return launch_status("align_avg_bwd_gather");
 }
 

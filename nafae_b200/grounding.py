@@ -105,8 +105,13 @@ def ground(vis_feats, word_feats, entities_length, Na, Nb, Ne, Delta, vis_lam, t
     """Functional form.  ``entities_length``: list of ints (as in the reference) or an int32 CUDA
     tensor (no H2D copy).  Returns (D_ind int64 (Na*Ns, Na*Ne), D_sim f32, margin_loss 0-dim).
     ``tensor_cores``: run the regions x queries contraction as tcgen05 tf32x3 tiles
-    (`nafae_ground_forward_tc`: same picks, D_sim / loss within 2e-4 relative)."""
+    (`nafae_ground_forward_tc`: same picks, D_sim / loss within 2e-4 relative); "auto" chooses by
+    shape from the measured A/B."""
     _C.require_cuda(vis_feats, "vis_feats")
+    if tensor_cores == "auto":
+        # measured A/B (profiles/RESULTS.md): the tcgen05 form wins once there are hundreds of query
+        # columns (520 live columns: 51 us vs 377 us); at the reference's 104 slots the FMA form does
+        tensor_cores = int(Na) * int(Ne) >= TC_AUTO_MIN_COLUMNS and int(Nb) <= 128
     Ns = int(vis_feats.size(0) / Na / Nb)  # model.py:530
     dims = (int(Na), Ns, int(Nb), int(Ne), int(vis_feats.size(1)))
     lens = _lens_tensor(entities_length, vis_feats.device)
@@ -118,6 +123,7 @@ def ground(vis_feats, word_feats, entities_length, Na, Nb, Ne, Delta, vis_lam, t
 
 
 _DEFAULT_POOL = _WorkspacePool()
+TC_AUTO_MIN_COLUMNS = 256  # query slots (Na * Ne) from which tensor_cores="auto" picks the tcgen05 form
 
 
 class DVSA(torch.nn.Module):

@@ -56,14 +56,35 @@ def main():
     def bwd():
         featg.grad = None
         outg.backward(gy, retain_graph=True)
+    gin = torch.empty_like(feat)
+
+    def bwd_atomic():  # the reference's formulation: zero-fill + one atomicAdd per tap
+        gin.zero_()
+        st = _C.lib.nafae_roi_align_backward(_C.ptr(gy), None, 1 / 16., F, rois2.shape[0], c["H"], c["W"], c["C"], 7, 7,
+                                             _C.POOL_AVG, _C.ptr(rois2), _C.ptr(gin), 0, _C.stream())
+        assert st == 1
+
+    def bwd_gather():  # this package's default: cell-gather, no atomics, no zero-fill
+        st = _C.lib.nafae_roi_align_backward(_C.ptr(gy), None, 1 / 16., F, rois2.shape[0], c["H"], c["W"], c["C"], 7, 7,
+                                             _C.POOL_AVG, _C.ptr(rois2), _C.ptr(gin), _C.FLAG_OVERWRITE, _C.stream())
+        assert st == 1
     from nafae_b200.model.roi_pooling.modules.roi_pool import _RoIPooling
     pool = _RoIPooling(7, 7, 1 / 16.)
+    featp = feat.clone().requires_grad_(True)
+    outp = pool(featp, rois2)
+
+    def pool_bwd():
+        featp.grad = None
+        outp.backward(gy, retain_graph=True)
     for name, fn, nbytes in (
         ("proposal_tail", lambda: proposal_tail(props, scores, c["pre"], c["Nb"], 0.7), None),
         ("nms_batched(full)", lambda: nms_batched(torch.cat((props, scores.unsqueeze(2)), 2), 0.7), None),
         ("roi_align_avg", lambda: mod(feat, rois2), in_bytes + out_bytes),
-        ("roi_align_avg bwd", bwd, in_bytes + out_bytes),
+        ("roi_align_avg bwd (module)", bwd, in_bytes + out_bytes),
+        ("roi_align_avg bwd gather", bwd_gather, in_bytes + out_bytes),
+        ("roi_align_avg bwd atomics", bwd_atomic, in_bytes + out_bytes),
         ("roi_pool fwd", lambda: pool(feat, rois2), in_bytes + out_bytes),
+        ("roi_pool bwd (module)", pool_bwd, in_bytes + out_bytes),
     ):
         med, mn = timeit(fn, flush=flush)
         extra = ""
