@@ -460,10 +460,16 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     ab = algorithmic_bytes(steps[0].rois.cpu().numpy(), c)
     achieved = ab["total"] / (kern_us * 1e-6) / 1e9
+    # DRAM bytes of the dominant kernel from the committed ncu capture -- only while the kernel source
+    # still is the one that was profiled (tools/summarize_ncu.py stamps its hash)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.cfg, {}).get("align_pool_fwd_slab_dram_bytes")
+        import hashlib
+        ent = json.load(open(tp)).get(args.cfg, {})
+        sha = hashlib.sha256(open(os.path.join(ROOT, "nafae_b200", "csrc", "roi_align.cu"), "rb").read()).hexdigest()[:16]
+        if ent.get("align_pool_fwd_slab_source_sha") == sha:
+            traffic = ent.get("align_pool_fwd_slab_dram_bytes")
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=Wm,
                 ms_per_step=ms_total / K, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", config=workload_config(args.cfg, world),

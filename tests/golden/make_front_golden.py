@@ -61,14 +61,17 @@ def front(ns, cls_prob, deltas, im_info, feat_stride, scales, ratios):
 
 
 def make_case(seed, B, H, W, img_h, img_w, ties):
+    """Seeded RPN outputs made of exactly representable values only (integer draws scaled by powers of
+    two), so that every machine regenerates bit-identical inputs -- softmax / randn differ by an ulp
+    between CPU builds, which would reorder near-equal scores."""
     g = torch.Generator().manual_seed(seed)
     A = 12
-    logits = torch.randn(B, 2 * A, H, W, generator=g) * 2
-    cls_prob = torch.softmax(logits.view(B, 2, A * H, W), 1).view(B, 2 * A, H, W)          # rpn.py:87-90
+    fg = torch.randint(1, 1 << 20, (B, A, H, W), generator=g).float() / float(1 << 20)     # (0, 1)
+    cls_prob = torch.cat([1.0 - fg, fg], 1)                                               # bg | fg, rpn.py:87-90
     if ties:  # saturated and repeated probabilities, as a confident RPN produces them
         cls_prob[:, A:, :, : W // 2] = torch.round(cls_prob[:, A:, :, : W // 2] * 8) / 8
         cls_prob[:, A:, 0, :] = 1.0
-    deltas = torch.randn(B, 4 * A, H, W, generator=g) * 0.4
+    deltas = torch.randint(-(1 << 15), 1 << 15, (B, 4 * A, H, W), generator=g).float() / float(1 << 16)
     deltas[:, 2::4] *= 0.5
     deltas[:, 3::4] *= 0.5
     im_info = torch.tensor([[float(img_h), float(img_w), 1.0]] * B)

@@ -21,6 +21,7 @@ KEYS = [
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "l1tex__m_xbar2l1tex_read_sectors_mem_global_op_tma_ld.sum",
     "sm__cycles_active.avg", "sm__cycles_active.max", "sm__cycles_elapsed.max",
+    "sm__inst_executed_pipe_tensor.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
@@ -79,6 +80,12 @@ def full(src, dst, cfg):
     tp = os.path.join(os.path.dirname(dst), "ncu_traffic.json")
     cur = json.load(open(tp)) if os.path.exists(tp) else {}
     cur.setdefault(cfg, {}).update(traffic)
+    if any(k.startswith("align_pool_fwd_slab") for k in traffic):
+        # bench.py reports roofline.traffic only while the kernel source is the one that was profiled
+        import hashlib
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        src_path = os.path.join(root, "nafae_b200", "csrc", "roi_align.cu")
+        cur[cfg]["align_pool_fwd_slab_source_sha"] = hashlib.sha256(open(src_path, "rb").read()).hexdigest()[:16]
     json.dump(cur, open(tp, "w"), indent=1, sort_keys=True)
     print(open(dst).read()[:3000])
 
