@@ -60,7 +60,12 @@ def parse_args():
                     help="gradient all-reduce kernel: NVLS multimem (in-switch reduction) when the box supports "
                          "NVSwitch multicast, else the bulk-copy peer-memory kernel")
     ap.add_argument("--comm-sms", type=int, default=-1, help="SMs kept free for the all-reduce CTAs")
+    ap.add_argument("--tensor-cores", type=int, default=0,
+                    help="1: the R x Q x D contraction of the scoring kernel on tcgen05 (tf32x3 split, fp32 recheck of near ties)")
     ap.add_argument("--ar-ctas", type=int, default=-1, help="CTAs of the all-reduce kernel")
+    ap.add_argument("--ar-threads", type=int, default=-1, help="threads per all-reduce CTA (multicast: 256, 512, 1024)")
+    ap.add_argument("--comm-priority", type=int, default=-1,
+                    help="CUDA priority of the all-reduce branch's stream (-1 = high, 0 = same as the step's)")
     return ap.parse_args()
 
 
@@ -232,7 +237,7 @@ def run_ours(args):
     def make_step():
         return GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], c["C"], c["H"], c["W"], c["n"],
                              pre_nms_topn=c["pre"], Delta=c["Delta"], vis_lam=c["vis_lam"],
-                             train=c["train"], device=dev)
+                             train=c["train"], device=dev, tensor_cores=bool(args.tensor_cores))
 
     host = [synth.make_batch(args.cfg, 1234 + 10 * rank + i) for i in range(2)]
     steps = [make_step() for _ in range(2)]
@@ -246,8 +251,9 @@ def run_ours(args):
             buckets = [parallel.GradBucket(parallel.trainable_grad_elems(), dev, world) for _ in range(2)]
         else:
             kw = dict(num_ctas=args.ar_ctas) if args.ar_ctas > 0 else {}
+            mkw = dict(kw, cta_threads=args.ar_threads) if args.ar_threads > 0 else kw
             buckets = [parallel.make_allreduce(parallel.trainable_grad_elems(), dev, kind=args.allreduce,
-                                               peer_kw=kw, mc_kw=kw) for _ in range(2)]
+                                               peer_kw=kw, mc_kw=mkw) for _ in range(2)]
         for st, b in zip(steps, buckets):
             st.grad_word = b.views([(st.NQ, c["D"])])[0]
     if world > 1:
@@ -265,6 +271,8 @@ def run_ours(args):
         ar_kind = "nccl" if args.nccl_allreduce else buckets[0].kind
         if args.comm_sms >= 0:
             comm_sms = args.comm_sms
+        elif ar_kind == "multicast" and buckets[0].cta_threads <= 256 and pipelined:
+            comm_sms = 0  # 256 threads x <= 48 registers: one such CTA co-resides with a RoIAlign CTA on its SM
         elif ar_kind == "multicast":
             # 512-thread CTAs without shared memory: two per SM
             comm_sms = (buckets[0].num_ctas * buckets[0].cta_threads + 1023) // 1024
@@ -277,7 +285,7 @@ def run_ours(args):
     # CTAs of the persistent RoIAlign kernel in the timed loops below (step graphs AND kernel-alone)
     slab_ctas = int(_C.lib.nafae_roi_align_persistent_ctas(steps[0].F * (c["C"] // 8)))
     side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-    comm = torch.cuda.Stream(dev) if world > 1 else None
+    comm = torch.cuda.Stream(dev, priority=args.comm_priority) if world > 1 else None
     for st, hb in zip(steps, host):
         st.load(hb)
         st.run()  # warm-up, produces valid state for the first pipelined replay

@@ -45,8 +45,10 @@ typedef struct CUstream_st* cudaStream_t; /* same opaque handle as CUDA driver_t
                                   A operand of the bridge GEMM (nafae_gemm_bf16_tn) written directly,
                                   half the output bytes; bandwidth-kernel shapes only */
 #define NAFAE_FLAG_OVERWRITE 8u /* nafae_roi_align_backward: bottom_diff is OVERWRITTEN (it need not be
-                                   zero-filled).  RoIAlignAvg 7x7 then runs the atomic-free cell-gather
-                                   kernel: every cell written once, deterministic */
+                                   zero-filled): every cell is written exactly once */
+#define NAFAE_FLAG_DETERMINISTIC 16u /* nafae_roi_align_backward (RoIAlignAvg 7x7): fixed summation
+                                        order, bitwise reproducible (cell-gather kernel, no atomics);
+                                        slower than the default shared-memory scatter */
 #define NAFAE_FLAG_EXACT 1u /* reference-order arithmetic (mixed fp32/fp64 exactly as the
                                reference kernel evaluates it): bit-identical pooled features,
                                slower.  Default (0) = fp32 FMA path, <= 1e-4 relative. */
@@ -180,9 +182,13 @@ int nafae_roi_align_forward(const float* bottom_data, float spatial_scale, int b
  * the pool's backward that autograd derives).  top_diff (R, C, out_height, out_width);
  * bottom_data is only read for NAFAE_POOL_MAX (may be NULL otherwise).  ACCUMULATES into
  * bottom_diff (B, C, H, W), which the caller zero-fills (functions/roi_align.py:38-39) -- unless
- * NAFAE_FLAG_OVERWRITE is set: then bottom_diff is fully written by the call (no zero-fill needed),
- * and the RoIAlignAvg 7x7 case uses a kernel without atomics in which a CTA owns a (frame, 8-channel)
- * slab of bottom_diff and every thread gathers its own cells (fixed summation order). */
+ * NAFAE_FLAG_OVERWRITE is set: then bottom_diff is fully written by the call (no zero-fill needed).
+ * RoIAlignAvg 7x7 (the configuration the reference instantiates) never sends an atomic to HBM: a CTA
+ * owns a (frame, 8-channel) slab of bottom_diff in shared memory, scatters the frame's RoIs into it and
+ * stores (OVERWRITE) or reduce-adds (default) the slab with bulk async copies.  Like the reference's
+ * atomicAdd the summation order is not fixed; NAFAE_FLAG_DETERMINISTIC selects a cell-gather kernel
+ * with a fixed order instead.  NAFAE_FLAG_EXACT and every other shape use the reference-style
+ * global-atomic kernel. */
 int nafae_roi_align_backward(const float* top_diff, const float* bottom_data, float spatial_scale,
                              int batch_size, int num_rois, int height, int width, int channels,
                              int out_height, int out_width, int pool_mode, const float* bottom_rois,

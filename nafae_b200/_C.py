@@ -115,6 +115,7 @@ FLAG_EXACT = 1
 FLAG_NO_GATE = 2
 FLAG_OUT_BF16 = 4
 FLAG_OVERWRITE = 8
+FLAG_DETERMINISTIC = 16
 GATE_BYTES = 32
 ROI_ALIGN_WS_BYTES = 64
 

@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) allreduce_tma_kernel(const ArP
     fence_mbar_init();
   }
   cta_barrier_all_ranks(p, 0, epoch);  // includes __syncthreads on both sides
+  cta_trace.mark_a();
 
   auto chunk_len4 = [&](int i) { return (int)min((long long)kChunk4, c_end - (c_begin + (long long)i * kChunk4)); };
   // the peers' copies of chunk i -> ring slot i % stages.  V = 0: thread 0 alone; V = 1: all of warp 0
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) allreduce_tma_kernel(const ArP
       bulk_commit();
     }
   }
+  cta_trace.mark_b();
   if (issuer) {
     bulk_wait_all<0>();  // every push has been performed
     asm volatile("fence.proxy.async;" ::: "memory");
@@ -450,6 +452,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_mc_kernel(const McParams p
   };
 
   barrier_all_ranks(0);
+  cta_trace.mark_a();
 
   {
     char* data = p.mc + kArHeaderBytes + ((size_t)p.rank * (size_t)slice4) * sizeof(float4);
@@ -473,6 +476,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_mc_kernel(const McParams p
       }
     }
   }
+  cta_trace.mark_b();
   __threadfence_system();  // my multicast stores are performed everywhere before I arrive
   barrier_all_ranks(2);
 

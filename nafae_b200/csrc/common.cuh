@@ -141,6 +141,13 @@ struct CtaTrace {
       g_cta_rec[slot].b += b;
     }
   }
+  // thread 0: phase stamps, ns since the CTA started, into the record's a / b counters
+  __device__ __forceinline__ void mark_a() {
+    if (idx >= 0 && idx < kCtaRecMax) g_cta_rec[idx].a = (int)(global_ns() - g_cta_rec[idx].t0);
+  }
+  __device__ __forceinline__ void mark_b() {
+    if (idx >= 0 && idx < kCtaRecMax) g_cta_rec[idx].b = (int)(global_ns() - g_cta_rec[idx].t0);
+  }
   __device__ __forceinline__ ~CtaTrace() {
     if (idx >= 0 && idx < kCtaRecMax) g_cta_rec[idx].t1 = global_ns();
   }
@@ -163,6 +170,8 @@ struct CtaTrace {
 struct CtaTrace {
   __device__ __forceinline__ void publish(int*) {}
   static __device__ __forceinline__ void count(int, int, int) {}
+  __device__ __forceinline__ void mark_a() {}
+  __device__ __forceinline__ void mark_b() {}
 };
 #define NAFAE_CTA_TRACE(name, kernel) [[maybe_unused]] ::nafae::CtaTrace name
 #define NAFAE_CTA_TRACE_READER(fn)

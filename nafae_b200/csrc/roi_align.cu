@@ -706,6 +706,8 @@ int try_launch_slab(const float* bottom, float scale, int B, int R, int H, int W
 
 }  // namespace
 // roi_align_bwd.cu: cell-gather backward without atomics (1 launched, 0 not eligible, < 0 error)
+int try_launch_avg_bwd_scatter(const float* top_diff, float scale, int B, int R, int H, int W, int C,
+                               const float* rois, float* bottom_diff, bool accumulate, cudaStream_t stream);
 int try_launch_avg_bwd_gather(const float* top_diff, float scale, int B, int R, int H, int W, int C,
                               const float* rois, float* bottom_diff, cudaStream_t stream);
 namespace {
@@ -796,14 +798,24 @@ NAFAE_API int nafae_roi_align_backward(const float* top_diff, const float* botto
   const int sh = pool_mode ? out_height + 1 : out_height, sw = pool_mode ? out_width + 1 : out_width;
   const long long total = (long long)num_rois * channels * sh * sw;
   const bool overwrite = (flags & NAFAE_FLAG_OVERWRITE) != 0;
+  const bool fast_avg = total > 0 && batch_size > 0 && !(flags & NAFAE_FLAG_EXACT) && pool_mode == NAFAE_POOL_AVG &&
+                        out_height == kOut && out_width == kOut && top_diff && bottom_rois && bottom_diff &&
+                        height >= 2 && width >= 2;
+  if (fast_avg) {
+    int st = 0;
+    if (overwrite && (flags & NAFAE_FLAG_DETERMINISTIC))
+      st = try_launch_avg_bwd_gather(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
+                                     bottom_rois, bottom_diff, stream);
+    if (st == 0)
+      st = try_launch_avg_bwd_scatter(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
+                                      bottom_rois, bottom_diff, !overwrite, stream);
+    if (st == 0 && overwrite)
+      st = try_launch_avg_bwd_gather(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
+                                     bottom_rois, bottom_diff, stream);
+    if (st != 0) return st;
+  }
   if (overwrite && batch_size > 0 && channels > 0) {
     NAFAE_REQUIRE(bottom_diff && height >= 1 && width >= 1, "roi_align backward: NULL / empty bottom_diff");
-    if (total > 0 && !(flags & NAFAE_FLAG_EXACT) && pool_mode == NAFAE_POOL_AVG && out_height == kOut &&
-        out_width == kOut && top_diff && bottom_rois) {
-      const int st = try_launch_avg_bwd_gather(top_diff, spatial_scale, batch_size, num_rois, height, width,
-                                               channels, bottom_rois, bottom_diff, stream);
-      if (st != 0) return st;
-    }
     cudaError_t e = cudaMemsetAsync(bottom_diff, 0, sizeof(float) * (size_t)batch_size * channels * height * width,
                                     stream);
     if (e != cudaSuccess) {

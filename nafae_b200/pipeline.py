@@ -148,7 +148,8 @@ class GroundingStep(object):
         self.run_head(backward)
 
     def kernels_per_step(self):
-        return self.KERNELS_PER_STEP_TRAIN if self.train else self.KERNELS_PER_STEP_EVAL
+        # the tcgen05 scoring path is two kernels (ground_p1_tc_kernel, ground_p23_kernel) instead of ground_fwd
+        return (self.KERNELS_PER_STEP_TRAIN if self.train else self.KERNELS_PER_STEP_EVAL) + int(self.tensor_cores)
 
     def capture(self):
         """Capture run() into a CUDA graph (launch-bound at this size: 5 kernels, ~100 us)."""

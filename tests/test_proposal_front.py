@@ -43,10 +43,10 @@ def test_front_end_matches_reference_functions(path):
                                                  bool(z["ties"]))
     dev = torch.device("cuda:0")
     anchors = torch.from_numpy(z["anchors"])
-    props, scores, order = proposal_front(cls_prob.to(dev), deltas.to(dev), im_info, anchors, 16, 6000,
-                                          return_order=True)
-    torch.cuda.synchronize()
     n = H * W * 12
+    props, scores, order = proposal_front(cls_prob.to(dev), deltas.to(dev), im_info, anchors, 16, n,
+                                          return_order=True)  # pre_nms_topN = everything: the whole order is checked
+    torch.cuda.synchronize()
     assert props.shape == (B, n, 4)
     k = z["order"].shape[1]
     np.testing.assert_array_equal(order.cpu().numpy()[:, :k], z["order"])                 # ties included

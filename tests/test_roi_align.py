@@ -171,6 +171,43 @@ def test_avg_backward_through_module_matches_oracle(name, F, C, H, W, per_frame,
 
 
 @gpu
+@pytest.mark.parametrize("name,F,C,H,W,per_frame,shuffle", [
+    ("cfg2_like", 4, 32, 38, 50, [20] * 4, False),
+    ("ragged_shuffled_empty_frame", 5, 16, 38, 50, [3, 0, 40, 1, 17], True),
+    ("more_than_one_id_table", 2, 8, 14, 14, [300, 131], True),
+    ("odd_width", 2, 8, 20, 37, [9, 12], False),
+])
+def test_avg_backward_kernels_through_the_c_abi(name, F, C, H, W, per_frame, shuffle):
+    """nafae_roi_align_backward for RoIAlignAvg 7x7: the shared-memory scatter overwriting and
+    accumulating (cp.reduce bulk add onto a non-zero tensor), the deterministic cell-gather (bitwise
+    reproducible) and the reference-style global-atomic kernel all agree with the oracle."""
+    from nafae_b200 import _C
+    rs = np.random.RandomState(abs(hash(name)) % 1000)
+    feat_shape = (F, C, H, W)
+    rois = _frame_rois(rs, F, per_frame, H * 16, W * 16, shuffle)
+    gy = rs.randn(rois.shape[0], C, 7, 7).astype(np.float32)
+    ref = ocpu.roi_align_avg_backward(gy, np.zeros(feat_shape, np.float32), rois, 1 / 16.)
+    tol = dict(rtol=RTOL, atol=RTOL * np.abs(ref).max())
+    g, r = _t(gy), _t(rois)
+
+    def call(out, flags):
+        st = _C.lib.nafae_roi_align_backward(_C.ptr(g), None, 1 / 16., F, rois.shape[0], H, W, C, 7, 7, _C.POOL_AVG,
+                                             _C.ptr(r), _C.ptr(out), flags, _C.stream())
+        assert st == 1
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    nan = lambda: torch.full(feat_shape, float("nan"), device=_dev())
+    np.testing.assert_allclose(call(nan(), _C.FLAG_OVERWRITE), ref, **tol)
+    base = rs.randn(*feat_shape).astype(np.float32)
+    np.testing.assert_allclose(call(_t(base.copy()), 0), base + ref, **tol)                      # accumulate
+    np.testing.assert_allclose(call(_t(base.copy()), _C.FLAG_EXACT), base + ref, **tol)          # global atomics
+    det = call(nan(), _C.FLAG_OVERWRITE | _C.FLAG_DETERMINISTIC)
+    np.testing.assert_allclose(det, ref, **tol)
+    assert np.array_equal(det, call(nan(), _C.FLAG_OVERWRITE | _C.FLAG_DETERMINISTIC))
+
+
+@gpu
 def test_out_of_range_batch_index_rows_are_zero():
     _, RoIAlignAvg, _ = _mods()
     rs = np.random.RandomState(2)

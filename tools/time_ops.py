@@ -58,16 +58,18 @@ def main():
         outg.backward(gy, retain_graph=True)
     gin = torch.empty_like(feat)
 
-    def bwd_atomic():  # the reference's formulation: zero-fill + one atomicAdd per tap
-        gin.zero_()
-        st = _C.lib.nafae_roi_align_backward(_C.ptr(gy), None, 1 / 16., F, rois2.shape[0], c["H"], c["W"], c["C"], 7, 7,
-                                             _C.POOL_AVG, _C.ptr(rois2), _C.ptr(gin), 0, _C.stream())
-        assert st == 1
-
-    def bwd_gather():  # this package's default: cell-gather, no atomics, no zero-fill
-        st = _C.lib.nafae_roi_align_backward(_C.ptr(gy), None, 1 / 16., F, rois2.shape[0], c["H"], c["W"], c["C"], 7, 7,
-                                             _C.POOL_AVG, _C.ptr(rois2), _C.ptr(gin), _C.FLAG_OVERWRITE, _C.stream())
-        assert st == 1
+    def raw_bwd(flags, zero):
+        def fn():
+            if zero:
+                gin.zero_()
+            st = _C.lib.nafae_roi_align_backward(_C.ptr(gy), None, 1 / 16., F, rois2.shape[0], c["H"], c["W"], c["C"],
+                                                 7, 7, _C.POOL_AVG, _C.ptr(rois2), _C.ptr(gin), flags, _C.stream())
+            assert st == 1
+        return fn
+    bwd_atomic = raw_bwd(_C.FLAG_EXACT, True)   # the reference's formulation: zero-fill + one global atomicAdd per tap
+    bwd_scatter = raw_bwd(_C.FLAG_OVERWRITE, False)  # default: shared-memory slab scatter, bulk store
+    bwd_scatter_acc = raw_bwd(0, True)          # same, reduce-added onto a zero-filled tensor
+    bwd_gather = raw_bwd(_C.FLAG_OVERWRITE | _C.FLAG_DETERMINISTIC, False)  # cell-gather, fixed summation order
     from nafae_b200.model.roi_pooling.modules.roi_pool import _RoIPooling
     pool = _RoIPooling(7, 7, 1 / 16.)
     featp = feat.clone().requires_grad_(True)
@@ -81,8 +83,10 @@ def main():
         ("nms_batched(full)", lambda: nms_batched(torch.cat((props, scores.unsqueeze(2)), 2), 0.7), None),
         ("roi_align_avg", lambda: mod(feat, rois2), in_bytes + out_bytes),
         ("roi_align_avg bwd (module)", bwd, in_bytes + out_bytes),
-        ("roi_align_avg bwd gather", bwd_gather, in_bytes + out_bytes),
-        ("roi_align_avg bwd atomics", bwd_atomic, in_bytes + out_bytes),
+        ("roi_align_avg bwd scatter", bwd_scatter, in_bytes + out_bytes),
+        ("roi_align_avg bwd zero+scatter-add", bwd_scatter_acc, in_bytes + out_bytes),
+        ("roi_align_avg bwd gather (determ.)", bwd_gather, in_bytes + out_bytes),
+        ("roi_align_avg bwd zero+global atomics", bwd_atomic, in_bytes + out_bytes),
         ("roi_pool fwd", lambda: pool(feat, rois2), in_bytes + out_bytes),
         ("roi_pool bwd (module)", pool_bwd, in_bytes + out_bytes),
     ):
@@ -91,7 +95,7 @@ def main():
         if nbytes:
             extra = "  %.0f GB/s (median) %.0f GB/s (best), alg bytes %.1f MB" % (
                 nbytes / med / 1e3, nbytes / mn / 1e3, nbytes / 1e6)
-        print("%-20s median %8.1f us  min %8.1f us%s" % (name, med, mn, extra))
+        print("%-38s median %8.1f us  min %8.1f us%s" % (name, med, mn, extra))
 
 
 if __name__ == "__main__":

@@ -20,17 +20,22 @@ dev = torch.device("cuda", local)
 steps = []
 for i in range(2):
     st = GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], c["C"], c["H"], c["W"], c["n"],
-                       pre_nms_topn=c["pre"], Delta=c["Delta"], vis_lam=c["vis_lam"], train=c["train"], device=dev)
+                       pre_nms_topn=c["pre"], Delta=c["Delta"], vis_lam=c["vis_lam"], train=c["train"], device=dev,
+                       tensor_cores=os.environ.get("TC") == "1")
     st.load(synth.make_batch(cfg, 1234 + i))
     st.run()
     steps.append(st)
 torch.cuda.synchronize()
 side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-comm = torch.cuda.Stream(dev)
+comm = torch.cuda.Stream(dev, priority=int(os.environ.get("COMM_PRIO", "-1")))
 buckets = None
 if world > 1:
-    buckets = [parallel.make_allreduce(parallel.trainable_grad_elems(), dev, kind=os.environ.get("AR_KIND", "auto"))
-               for _ in range(2)]
+    kw = {}
+    if os.environ.get("AR_CTAS"):
+        kw["num_ctas"] = int(os.environ["AR_CTAS"])
+    mkw = dict(kw, cta_threads=int(os.environ["AR_THREADS"])) if os.environ.get("AR_THREADS") else kw
+    buckets = [parallel.make_allreduce(parallel.trainable_grad_elems(), dev, kind=os.environ.get("AR_KIND", "auto"),
+                                       peer_kw=kw, mc_kw=mkw) for _ in range(2)]
     for st, b in zip(steps, buckets):
         st.grad_word = b.views([(st.NQ, c["D"])])[0]
         b.launch()
@@ -128,6 +133,11 @@ for (sa, sb) in segs[-2:]:
             if len(late):
                 lt0 = (late["t0"].astype(np.int64) - base) / 1e3
                 print("            late: start p50 %.1f max %.1f, their items p50 %d" % (np.percentile(lt0, 50), lt0.max(), np.percentile(late["a"], 50)))
+        if k == 5:
+            print("            phases per CTA (us since its start, p50 / max): first barrier passed %.1f / %.1f, data done %.1f / %.1f, exit %.1f / %.1f; co-resident with RoIAlign CTAs on %d SMs"
+                  % (np.percentile(x["a"], 50) / 1e3, x["a"].max() / 1e3, np.percentile(x["b"], 50) / 1e3, x["b"].max() / 1e3,
+                     np.percentile(t1 - t0, 50), (t1 - t0).max(),
+                     len(np.intersect1d(x["smid"], seg[seg["kernel"] == 1]["smid"]))))
         if k in (3, 4):  # long-lived CTAs of the head kernels: where and when
             long_ = x[(t1 - t0) > 4]
             lt0 = (long_["t0"].astype(np.int64) - base) / 1e3
