@@ -47,11 +47,15 @@ def parse_args():
                     help="run the two halves of a step back to back instead of overlapping the head of "
                          "batch k with the detector half of batch k+1")
     ap.add_argument("--reserve-sms", type=int, default=-1)
-    ap.add_argument("--steps-per-graph", type=int, default=1,
-                    help="pipelined steps captured per CUDA graph (measured: 1 is fastest, 60.8 us/step vs "
-                         "63.7 us with 16 -- join/fork inside a graph costs more than back-to-back replays)")
+    ap.add_argument("--steps-per-graph", type=int, default=-1,
+                    help="pipelined steps captured per CUDA graph; -1 (default) = 1 on one GPU (54.5 vs 54.8 us/step "
+                         "with 4) and 4 on several: the ranks meet in the all-reduce every step, and host-side replay "
+                         "gaps (4-8 us, jittery) make one rank late for all -- 62.7 -> 59.9 us/step at 8 GPUs")
     ap.add_argument("--no-gate", action="store_true",
                     help="do not hold the all-reduce branch behind the RoIAlign kernel's residency gate")
+    ap.add_argument("--gate", action="store_true",
+                    help="hold the all-reduce branch behind the gate (default for the peer-memory kernel; the NVLS "
+                         "kernel's 8 CTAs start at once on the SMs reserved for them)")
     ap.add_argument("--gate-head", action="store_true",
                     help="also hold the head branch behind the gate (measured slower)")
     ap.add_argument("--nccl-allreduce", action="store_true",
@@ -60,8 +64,11 @@ def parse_args():
                     help="gradient all-reduce kernel: NVLS multimem (in-switch reduction) when the box supports "
                          "NVSwitch multicast, else the bulk-copy peer-memory kernel")
     ap.add_argument("--comm-sms", type=int, default=-1, help="SMs kept free for the all-reduce CTAs")
-    ap.add_argument("--tensor-cores", type=int, default=0,
-                    help="1: the R x Q x D contraction of the scoring kernel on tcgen05 (tf32x3 split, fp32 recheck of near ties)")
+    ap.add_argument("--tensor-cores", type=int, default=-1,
+                    help="1: the R x Q x D contraction of the scoring kernel on tcgen05 (tf32x3 split, fp32 recheck of "
+                         "near ties); 0: fp32 FMA kernel; -1 (default): tcgen05 in the pipelined step -- its 7 CTAs "
+                         "leave the SMs to the concurrent RoIAlign kernel (54.5 vs 58.7 us / step) -- and FMA in the "
+                         "sequential one, where latency decides (16 vs 30 us)")
     ap.add_argument("--ar-ctas", type=int, default=-1, help="CTAs of the all-reduce kernel")
     ap.add_argument("--ar-threads", type=int, default=-1, help="threads per all-reduce CTA (multicast: 256, 512, 1024)")
     ap.add_argument("--comm-priority", type=int, default=-1,
@@ -237,7 +244,8 @@ def run_ours(args):
     def make_step():
         return GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], c["C"], c["H"], c["W"], c["n"],
                              pre_nms_topn=c["pre"], Delta=c["Delta"], vis_lam=c["vis_lam"],
-                             train=c["train"], device=dev, tensor_cores=bool(args.tensor_cores))
+                             train=c["train"], device=dev,
+                             tensor_cores=(not args.no_pipeline) if args.tensor_cores < 0 else bool(args.tensor_cores))
 
     host = [synth.make_batch(args.cfg, 1234 + 10 * rank + i) for i in range(2)]
     steps = [make_step() for _ in range(2)]
@@ -280,6 +288,14 @@ def run_ours(args):
             comm_sms = 0  # the 128-thread all-reduce CTAs co-reside with the slab CTAs instead
         else:
             comm_sms = parallel.COMM_SMS
+    # the all-reduce branch waits for the RoIAlign kernel's residency gate?  peer kernel: yes (16 one-per-SM CTAs
+    # must not take SMs the persistent kernel was sized for); NVLS kernel: no (8 small CTAs, 8 SMs set aside)
+    gated = pipelined and world > 1 and not args.no_gate and (args.gate or ar_kind != "multicast")
+    if world > 1 and ar_kind == "multicast" and not gated and args.comm_sms < 0 and pipelined and \
+            buckets[0].cta_threads > 256:
+        comm_sms = buckets[0].num_ctas  # ungated CTAs arrive on an empty GPU: one per SM
+    if args.steps_per_graph < 0:
+        args.steps_per_graph = 4 if (world > 1 and pipelined) else 1
     reserve = args.reserve_sms if args.reserve_sms >= 0 else (HEAD_SMS if pipelined else 0) + comm_sms
     _C.lib.nafae_set_reserved_sms(reserve)
     # CTAs of the persistent RoIAlign kernel in the timed loops below (step graphs AND kernel-alone)
@@ -307,7 +323,7 @@ def run_ours(args):
                 return None
             comm.wait_stream(cur)
             with torch.cuda.stream(comm):
-                if pipelined and not args.no_gate:
+                if gated:
                     steps[j].wait_gate(1)  # spread over the reserved SMs only (see nafae_gate_wait)
                 allreduce(buckets[j])
             return comm
@@ -333,7 +349,7 @@ def run_ours(args):
                     return None
                 comm.wait_stream(cur)
                 with torch.cuda.stream(comm):
-                    if not args.no_gate:
+                    if gated:
                         steps[j].wait_gate(1)
                     allreduce(buckets[j])
                 return comm
@@ -494,6 +510,8 @@ def run_ours(args):
         "depend on earlier weight updates; %d SMs reserved from the persistent RoIAlign kernel"
         % (S, " || gradient all-reduce" if world > 1 else "", reserve)) if pipelined else (
         "sequential: one CUDA graph per step, five kernels back to back")
+    line["config"]["head"] = ("scoring contraction on tcgen05 (tf32x3 split, near-ties rechecked in fp32: picks bit-exact)"
+                              if steps[0].tensor_cores else "scoring contraction on the fp32 FMA pipe")
     if world > 1:
         line["replicas_identical"] = replicas_identical
         line["config"]["allreduce_kind"] = ar_kind
@@ -501,26 +519,28 @@ def run_ours(args):
         line["config"]["allreduce"] = (
             "NVLS all-reduce (AVG) per step over a flat fp32 bucket of %d elems (%.1f MB): allreduce_mc_kernel, "
             "multimem.ld_reduce in the NVSwitch + multimem.st broadcast, %d CTAs x %d threads, a parallel branch "
-            "of the NEXT step's CUDA graph behind the RoIAlign kernel's residency gate; %d SMs left free for it"
+            "of the NEXT step's CUDA graph on a high-priority stream%s; %d SMs left free for it"
             % (parallel.trainable_grad_elems(), parallel.trainable_grad_elems() * 4 / 1e6,
-               buckets[0].num_ctas, buckets[0].cta_threads, comm_sms))
-        line["gpu_launches"] = K * (steps[0].kernels_per_step() + 1 + (1 if pipelined and not args.no_gate else 0))
+               buckets[0].num_ctas, buckets[0].cta_threads,
+               " behind the RoIAlign kernel's residency gate" if gated else "", comm_sms))
+        line["gpu_launches"] = K * (steps[0].kernels_per_step() + 1 + (1 if gated else 0))
     elif world > 1:
-        line["config"]["allreduce"] = ("%s all-reduce (AVG) per step over a flat fp32 bucket of %d elems (%.1f MB), "
-                                       "a parallel branch of the NEXT step's CUDA graph (overlaps its "
-                                       "NMS/RoIAlign, launched behind the RoIAlign kernel's residency gate); "
-                                       "%d SMs left free for it"
-                                       % ("NCCL" if args.nccl_allreduce else
-                                          ("fused two-shot NVLink peer-memory kernel (allreduce_tma_kernel: bulk-copy pull, "
-                                           "reduce, bulk-copy push; %d CTAs)" % buckets[0].num_ctas)
-                                          if buckets[0].cta_threads == 0 else
-                                          "two-shot NVLink peer-memory kernel (allreduce_avg_kernel, %d CTAs x %d threads)"
-                                          % (buckets[0].num_ctas, buckets[0].cta_threads),
-                                          parallel.trainable_grad_elems(), parallel.trainable_grad_elems() * 4 / 1e6,
-                                          comm_sms))
+        if args.nccl_allreduce:
+            ar_name = "NCCL"
+        elif buckets[0].cta_threads == 0:
+            ar_name = ("fused two-shot NVLink peer-memory kernel (allreduce_tma_kernel: bulk-copy pull, reduce, "
+                       "bulk-copy push; %d CTAs)" % buckets[0].num_ctas)
+        else:
+            ar_name = ("two-shot NVLink peer-memory kernel (allreduce_avg_kernel, %d CTAs x %d threads)"
+                       % (buckets[0].num_ctas, buckets[0].cta_threads))
+        line["config"]["allreduce"] = (
+            "%s all-reduce (AVG) per step over a flat fp32 bucket of %d elems (%.1f MB), a parallel branch of the NEXT "
+            "step's CUDA graph on a high-priority stream (overlaps its NMS/RoIAlign%s); %d SMs left free for it"
+            % (ar_name, parallel.trainable_grad_elems(), parallel.trainable_grad_elems() * 4 / 1e6,
+               ", launched behind the RoIAlign kernel's residency gate" if gated else "", comm_sms))
         # + the all-reduce kernel (ours unless NCCL) + the one-warp gate kernel in front of it
         line["gpu_launches"] = K * (steps[0].kernels_per_step() + (0 if args.nccl_allreduce else 1) +
-                                    (1 if pipelined and not args.no_gate else 0))
+                                    (1 if gated else 0))
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

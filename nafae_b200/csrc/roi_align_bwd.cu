@@ -1,15 +1,14 @@
-// RoIAlignAvg backward WITHOUT atomics (sm_100a): cell-gather with exclusive ownership.
+// RoIAlignAvg backward without global atomics (sm_100a).
 //
 // Reference: ROIAlignBackward (lib/model/roi_align/src/roi_align_kernel.cu:94-143) scatters every
 // sample's gradient to four cells with atomicAdd into a pre-zeroed (B, C, H, W) tensor, preceded by
-// avg_pool2d's backward (autograd); at cfg2 that is 26 M float atomics and a 156 MB memset.
-// Here a CTA owns one (frame, 8-channel) slab of bottom_diff outright: every thread owns a few
-// CELLS of that slab for all 8 channels and GATHERS what the frame's RoIs send there, so the output
-// is written exactly once, coalesced, with plain stores -- no atomics, no zero-fill, a fixed summation
-// order (deterministic).  Which samples of a RoI reach a cell is separable: sample row ph reaches cell
-// row y with weight (1 - h_ratio) when hstart[ph] == y and h_ratio when hstart[ph] == y - 1 (ranges
-// of ph, monotone), likewise for columns; two byte-tables per RoI (rows, columns) make the test two
-// shared-memory reads, and most (RoI, cell) pairs are rejected by them.
+// avg_pool2d's backward (autograd); at cfg2 that is 105 M float atomics to L2 and a 156 MB memset.
+// Both kernels here give a CTA exclusive ownership of (frame, 8-channel) slabs of bottom_diff, so HBM
+// sees every output byte once, written with plain / bulk stores:
+//   align_avg_bwd_scatter  (default)  the slab lives in shared memory, RoIs are scattered into it with
+//                          shared-memory atomics, the finished slab leaves by bulk async copy;
+//   align_avg_bwd_gather   (NAFAE_FLAG_DETERMINISTIC)  threads own cells and gather their contributions
+//                          from a per-frame index; fixed summation order, bitwise reproducible.
 // The pool's backward is folded in: sample gradient gs[ph][pw] = sum of the <= 4 output gradients
 // whose 2x2 window contains the sample, the 1/4 sits in the column weights.
 //
@@ -24,10 +23,8 @@ constexpr int kS = 8, kOut = 7;
 constexpr int kBwCg = 8;          // channels per pass
 constexpr int kBwThreads = 512;
 constexpr int kBwWarps = kBwThreads / 32;
-constexpr int kBwChunk = 24;      // RoIs whose tables / gradients are resident at a time
 constexpr int kBwCells = 4;       // cells per thread  => H*W <= 2048
 constexpr int kBwMaxDim = 128;    // H, W <= 128
-constexpr int kBwGroups = 4;      // channel groups (of kBwCg) a CTA works through with one set of tables
 
 struct BwAxis {  // per RoI
   int hcell[kS];   // cell row of sample row ph (hstart), -1000 when the sample row is outside
@@ -111,25 +108,47 @@ __device__ __forceinline__ void fill_axis(BwAxis* a, const float* __restrict__ r
   }
 }
 
-// Two CTAs per SM (<= 64 registers, ~85 KB of shared memory each): one CTA's global round trips
-// (RoI scan, gradient staging) hide behind the other's gather.
+// ------------------------------------------------------------------ indexed cell-gather (deterministic) ----
+// Which (RoI, sample) pairs reach a cell depends on the frame's RoIs only, not on the channel: a CTA
+// builds that index ONCE per frame -- per cell the list of (sample slot, weight) contributions in
+// (RoI, sample row, sample column) order, a CSR over the H x W cells -- and reuses it for every
+// 8-channel group it owns.  Building enumerates (cell, RoI) pairs through the two byte-tables; the
+// per-group work is then exactly the contributions (20 RoIs x 256 at cfg2), no tests.  Threads own
+// cells (coalesced, exclusive stores); cells with more than kCsrLong contributions (RoIs piled on one
+// spot, e.g. the zero-padded proposal rows) are reduced by a whole warp with a fixed shuffle tree.
+// The grid is persistent: CTA b takes the contiguous unit range [b, b + 1) * units / grid of the
+// (frame, channel group) units, so a CTA sees at most two frames and rebuilds the index that often.
+constexpr int kCsrChunk = 20;                   // RoIs indexed at a time
+constexpr int kCsrMaxEnt = kCsrChunk * 256;     // 64 samples x 4 cells per RoI
+constexpr int kCsrLong = 48;                    // contributions per cell above which a warp takes the cell
+constexpr int kCsrMaxLong = kCsrMaxEnt / (kCsrLong + 1) + 1;
+
+struct CsrEnt {
+  int slot;   // (RoI in chunk) * 64 + sample
+  float w;
+};
+struct CsrLong {
+  int cell, start, cnt;
+};
+
 __global__ void __launch_bounds__(kBwThreads, 2) align_avg_bwd_gather(const BwParams p) {
   extern __shared__ __align__(16) unsigned char bw_smem[];
-  float* gs = reinterpret_cast<float*>(bw_smem);                       // [chunk][64 samples][8 ch]
-  float* gst = gs + kBwChunk * 64 * kBwCg;                             // [chunk][8 ch][49]
-  BwAxis* ax = reinterpret_cast<BwAxis*>(gst + kBwChunk * kBwCg * 49); // [chunk]
-  uchar4* rowmap = reinterpret_cast<uchar4*>(ax + kBwChunk);           // [chunk][H]: lo0, n0, lo1, n1
-  uchar4* colmap = rowmap + kBwChunk * p.H;                            // [chunk][W]
-  __shared__ int s_ids[kBwChunk];
+  float* gs = reinterpret_cast<float*>(bw_smem);                        // [chunk][64 samples][8 ch]
+  CsrEnt* ent = reinterpret_cast<CsrEnt*>(gs + kCsrChunk * 64 * kBwCg); // [kCsrMaxEnt]
+  BwAxis* ax = reinterpret_cast<BwAxis*>(ent + kCsrMaxEnt);             // [chunk]
+  uchar4* rowmap = reinterpret_cast<uchar4*>(gs);                       // [chunk][H]: lo0, n0, lo1, n1 (aliases gs
+  uchar4* colmap = rowmap + kCsrChunk * p.H;                            // [chunk][W]   while the index is built)
+  __shared__ int s_ids[kCsrChunk];
   __shared__ int s_wcnt[kBwWarps];
-  __shared__ int s_n, s_next;
+  __shared__ int s_n, s_next, s_nlong;
+  __shared__ CsrLong s_long[kCsrMaxLong];
 
-  const int tid = threadIdx.x;
-  const int f = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
-  const int ch_per_split = p.C / p.splits;
-  const int ch_begin = split * ch_per_split;
-  const int ngroups = ch_per_split / kBwCg;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int groups = p.C / kBwCg;
   const int hw = p.H * p.W;
+  const long long units = (long long)p.B * groups;
+  long long u = units * blockIdx.x / gridDim.x;
+  const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
 
   int cy[kBwCells], cx[kBwCells];
 #pragma unroll
@@ -139,80 +158,83 @@ __global__ void __launch_bounds__(kBwThreads, 2) align_avg_bwd_gather(const BwPa
     cx[i] = cell < hw ? cell - (cell / p.W) * p.W : -1;
   }
 
-  int r_next = 0;
-  bool first_chunk = true;
-  for (;;) {
-    // ---- next chunk: the first kBwChunk RoIs of frame f at or after r_next, in index order
-    frame_rois(p.rois, p.R, f, r_next, kBwChunk, s_ids, s_wcnt, &s_n, &s_next);
-    const int n = s_n;
-    r_next = s_next;
-    if (n == 0 && !first_chunk) break;
-
-    // ---- per-RoI axis tables: one thread per (RoI, axis)
-    if (tid < 2 * n) {
-      fill_axis(&ax[tid >> 1], p.rois + (size_t)s_ids[tid >> 1] * 5, tid & 1, p.scale, p.H, p.W);
-    }
-    __syncthreads();
-    // ---- row / column maps: which sample rows reach cell row y with weight h0 (hstart == y) / h1
-    for (int i = tid; i < n * (p.H + p.W); i += kBwThreads) {
-      const int j = i / (p.H + p.W), k = i - j * (p.H + p.W);
-      const bool is_w = k >= p.H;
-      const int v = is_w ? k - p.H : k;
-      const int* cells = is_w ? ax[j].wcell : ax[j].hcell;
-      int lo0 = 0, n0 = 0, lo1 = 0, n1 = 0;
+  while (u < u_end) {
+    const int f = (int)(u / groups);
+    const int g_begin = (int)(u - (long long)f * groups);
+    const int g_end = (int)min((long long)groups, (long long)g_begin + (u_end - u));
+    int r_next = 0;
+    bool first_chunk = true;
+    for (;;) {
+      __syncthreads();  // the previous gather is done with gs / ent
+      frame_rois(p.rois, p.R, f, r_next, kCsrChunk, s_ids, s_wcnt, &s_n, &s_next);
+      const int n = s_n;
+      r_next = s_next;
+      if (n == 0 && !first_chunk) break;
+      if (tid < 2 * n) fill_axis(&ax[tid >> 1], p.rois + (size_t)s_ids[tid >> 1] * 5, tid & 1, p.scale, p.H, p.W);
+      if (tid == 0) s_nlong = 0;
+      __syncthreads();
+      // row / column maps: which sample rows reach cell row y with weight h0 (hstart == y) / h1 (hstart == y - 1)
+      for (int i = tid; i < n * (p.H + p.W); i += kBwThreads) {
+        const int j = i / (p.H + p.W), k = i - j * (p.H + p.W);
+        const bool is_w = k >= p.H;
+        const int v = is_w ? k - p.H : k;
+        const int* cells = is_w ? ax[j].wcell : ax[j].hcell;
+        int lo0 = 0, n0 = 0, lo1 = 0, n1 = 0;
 #pragma unroll
-      for (int s = 0; s < kS; ++s) {
-        const int cc = cells[s];
-        if (cc == v) {
-          if (n0 == 0) lo0 = s;
-          ++n0;
+        for (int q = 0; q < kS; ++q) {
+          const int cc = cells[q];
+          if (cc == v) {
+            if (n0 == 0) lo0 = q;
+            ++n0;
+          }
+          if (cc == v - 1) {
+            if (n1 == 0) lo1 = q;
+            ++n1;
+          }
         }
-        if (cc == v - 1) {
-          if (n1 == 0) lo1 = s;
-          ++n1;
-        }
-      }
-      const uchar4 m = make_uchar4((unsigned char)lo0, (unsigned char)n0, (unsigned char)lo1, (unsigned char)n1);
-      if (is_w) colmap[j * p.W + v] = m;
-      else rowmap[j * p.H + v] = m;
-    }
-
-    // ---- the channel groups of this CTA, all with the tables above
-    for (int g = 0; g < ngroups; ++g) {
-      const int c0 = ch_begin + g * kBwCg;
-      __syncthreads();  // previous group's gather is done with gs / gst (and the maps are complete)
-      // output gradients of the chunk -> shared (coalesced: 8 channels x 49 are contiguous per RoI)
-      for (int i = tid; i < n * kBwCg * 49; i += kBwThreads) {
-        const int j = i / (kBwCg * 49), rem = i - j * (kBwCg * 49);
-        gst[i] = __ldg(p.top_diff + ((size_t)s_ids[j] * p.C + c0) * 49 + rem);
-      }
-      // accumulators: zero for the first chunk of the frame, else what the earlier chunks left
-      float acc[kBwCells][kBwCg];
-#pragma unroll
-      for (int i = 0; i < kBwCells; ++i) {
-        const int cell = tid + i * kBwThreads;
-#pragma unroll
-        for (int c = 0; c < kBwCg; ++c)
-          acc[i][c] = (first_chunk || cell >= hw) ? 0.f : p.bottom_diff[((size_t)f * p.C + c0 + c) * hw + cell];
+        const uchar4 m = make_uchar4((unsigned char)lo0, (unsigned char)n0, (unsigned char)lo1, (unsigned char)n1);
+        if (is_w) colmap[j * p.W + v] = m;
+        else rowmap[j * p.H + v] = m;
       }
       __syncthreads();
-      // sample gradients: avg_pool2d(2, 1) backward, layout [RoI][sample][channel]
-      for (int i = tid; i < n * 64 * kBwCg; i += kBwThreads) {
-        const int c = i % kBwCg, s = (i / kBwCg) % 64, j = i / (kBwCg * 64);
-        const int ph = s >> 3, pw = s & 7;
-        const float* gg = gst + (j * kBwCg + c) * 49;
-        float v = 0.f;
-        if (ph > 0 && pw > 0) v += gg[(ph - 1) * kOut + pw - 1];
-        if (ph > 0 && pw < kOut) v += gg[(ph - 1) * kOut + pw];
-        if (ph < kOut && pw > 0) v += gg[ph * kOut + pw - 1];
-        if (ph < kOut && pw < kOut) v += gg[ph * kOut + pw];
-        gs[i] = v;
-      }
-      __syncthreads();
-      // gather: every owned cell collects from every RoI of the chunk
+      // pass 1: contributions per owned cell; exclusive scan in cell order -> start of every cell's list
+      int cnt[kBwCells], start[kBwCells];
 #pragma unroll
       for (int i = 0; i < kBwCells; ++i) {
-        if (cy[i] < 0) continue;
+        int t = 0;
+        if (cy[i] >= 0)
+          for (int j = 0; j < n; ++j) {
+            const uchar4 rm = rowmap[j * p.H + cy[i]], cm = colmap[j * p.W + cx[i]];
+            t += (rm.y + rm.w) * (cm.y + cm.w);
+          }
+        cnt[i] = t;
+      }
+      int carry = 0;
+#pragma unroll
+      for (int i = 0; i < kBwCells; ++i) {
+        int inc = cnt[i];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_wcnt[warp] = inc;
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int w = 0; w < kBwWarps; ++w) {
+          const int cw = s_wcnt[w];
+          if (w < warp) before += cw;
+          tot += cw;
+        }
+        start[i] = carry + before + inc - cnt[i];
+        carry += tot;
+        __syncthreads();
+      }
+      // pass 2: the lists, in (RoI, sample row, sample column) order
+#pragma unroll
+      for (int i = 0; i < kBwCells; ++i) {
+        if (cy[i] < 0 || cnt[i] == 0) continue;
+        int pos = start[i];
         for (int j = 0; j < n; ++j) {
           const uchar4 rm = rowmap[j * p.H + cy[i]];
           if (rm.y + rm.w == 0) continue;
@@ -224,35 +246,102 @@ __global__ void __launch_bounds__(kBwThreads, 2) align_avg_bwd_gather(const BwPa
             const float wy = rr < rm.y ? a.h0[ph] : a.h1[ph];
             for (int qq = 0; qq < cm.y + cm.w; ++qq) {
               const int pw = qq < cm.y ? cm.x + qq : cm.z + (qq - cm.y);
-              const float wgt = wy * (qq < cm.y ? a.w0[pw] : a.w1[pw]);
-              const float4* g4 = reinterpret_cast<const float4*>(gs + ((size_t)j * 64 + ph * 8 + pw) * kBwCg);
-              const float4 ga = g4[0], gb = g4[1];
-              acc[i][0] = fmaf(wgt, ga.x, acc[i][0]);
-              acc[i][1] = fmaf(wgt, ga.y, acc[i][1]);
-              acc[i][2] = fmaf(wgt, ga.z, acc[i][2]);
-              acc[i][3] = fmaf(wgt, ga.w, acc[i][3]);
-              acc[i][4] = fmaf(wgt, gb.x, acc[i][4]);
-              acc[i][5] = fmaf(wgt, gb.y, acc[i][5]);
-              acc[i][6] = fmaf(wgt, gb.z, acc[i][6]);
-              acc[i][7] = fmaf(wgt, gb.w, acc[i][7]);
+              CsrEnt e;
+              e.slot = j * 64 + ph * 8 + pw;
+              e.w = wy * (qq < cm.y ? a.w0[pw] : a.w1[pw]);
+              ent[pos++] = e;
             }
           }
         }
-      }
-      // every cell of the slab is written by its owner only (frames without RoIs: zeros)
-#pragma unroll
-      for (int i = 0; i < kBwCells; ++i) {
-        const int cell = tid + i * kBwThreads;
-        if (cell < hw) {
-#pragma unroll
-          for (int c = 0; c < kBwCg; ++c)
-            p.bottom_diff[((size_t)f * p.C + c0 + c) * hw + cell] = acc[i][c];
+        if (cnt[i] > kCsrLong) {
+          const int k = atomicAdd(&s_nlong, 1);  // at most kCsrMaxLong such cells exist; their order is irrelevant
+          CsrLong l;
+          l.cell = tid + i * kBwThreads;
+          l.start = start[i];
+          l.cnt = cnt[i];
+          s_long[k] = l;
         }
       }
+
+      // ---- the channel groups of this CTA's range in frame f, all with the index above
+      for (int g = g_begin; g < g_end; ++g) {
+        const int c0 = g * kBwCg;
+        __syncthreads();  // index complete / previous group's gather done with gs
+        // sample gradients = avg_pool2d(2, 1) backward of the output gradients, layout [RoI][sample][channel]
+        for (int i = tid; i < n * 64 * kBwCg; i += kBwThreads) {
+          const int sidx = i & 63, c = (i >> 6) & (kBwCg - 1), j = i >> 9;
+          const int ph = sidx >> 3, pw = sidx & 7;
+          const float* gg = p.top_diff + ((size_t)s_ids[j] * p.C + c0 + c) * (kOut * kOut);
+          float v = 0.f;
+          if (ph > 0 && pw > 0) v += __ldg(gg + (ph - 1) * kOut + pw - 1);
+          if (ph > 0 && pw < kOut) v += __ldg(gg + (ph - 1) * kOut + pw);
+          if (ph < kOut && pw > 0) v += __ldg(gg + ph * kOut + pw - 1);
+          if (ph < kOut && pw < kOut) v += __ldg(gg + ph * kOut + pw);
+          gs[((size_t)j * 64 + sidx) * kBwCg + c] = v;
+        }
+        __syncthreads();
+        float* out = p.bottom_diff + ((size_t)f * p.C + c0) * hw;
+        // short lists: the owning thread
+#pragma unroll
+        for (int i = 0; i < kBwCells; ++i) {
+          const int cell = tid + i * kBwThreads;
+          if (cell >= hw || cnt[i] > kCsrLong) continue;
+          float acc[kBwCg];
+#pragma unroll
+          for (int c = 0; c < kBwCg; ++c) acc[c] = first_chunk ? 0.f : out[(size_t)c * hw + cell];
+          for (int e = start[i]; e < start[i] + cnt[i]; ++e) {
+            const CsrEnt en = ent[e];
+            const float4* g4 = reinterpret_cast<const float4*>(gs + (size_t)en.slot * kBwCg);
+            const float4 ga = g4[0], gb = g4[1];
+            acc[0] = fmaf(en.w, ga.x, acc[0]);
+            acc[1] = fmaf(en.w, ga.y, acc[1]);
+            acc[2] = fmaf(en.w, ga.z, acc[2]);
+            acc[3] = fmaf(en.w, ga.w, acc[3]);
+            acc[4] = fmaf(en.w, gb.x, acc[4]);
+            acc[5] = fmaf(en.w, gb.y, acc[5]);
+            acc[6] = fmaf(en.w, gb.z, acc[6]);
+            acc[7] = fmaf(en.w, gb.w, acc[7]);
+          }
+#pragma unroll
+          for (int c = 0; c < kBwCg; ++c) out[(size_t)c * hw + cell] = acc[c];
+        }
+        // long lists: one warp per cell, lanes stride the list, fixed shuffle tree
+        for (int k = warp; k < s_nlong; k += kBwWarps) {
+          const CsrLong l = s_long[k];
+          float acc[kBwCg];
+#pragma unroll
+          for (int c = 0; c < kBwCg; ++c) acc[c] = 0.f;
+          for (int e = l.start + lane; e < l.start + l.cnt; e += 32) {
+            const CsrEnt en = ent[e];
+            const float4* g4 = reinterpret_cast<const float4*>(gs + (size_t)en.slot * kBwCg);
+            const float4 ga = g4[0], gb = g4[1];
+            acc[0] = fmaf(en.w, ga.x, acc[0]);
+            acc[1] = fmaf(en.w, ga.y, acc[1]);
+            acc[2] = fmaf(en.w, ga.z, acc[2]);
+            acc[3] = fmaf(en.w, ga.w, acc[3]);
+            acc[4] = fmaf(en.w, gb.x, acc[4]);
+            acc[5] = fmaf(en.w, gb.y, acc[5]);
+            acc[6] = fmaf(en.w, gb.z, acc[6]);
+            acc[7] = fmaf(en.w, gb.w, acc[7]);
+          }
+#pragma unroll
+          for (int c = 0; c < kBwCg; ++c) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
+          }
+          if (lane < kBwCg) {
+            float v = acc[0];
+#pragma unroll
+            for (int c = 1; c < kBwCg; ++c) v = lane == c ? acc[c] : v;
+            float* dst = out + (size_t)lane * hw + l.cell;
+            *dst = first_chunk ? v : *dst + v;
+          }
+        }
+      }
+      first_chunk = false;
+      if (r_next >= p.R) break;
     }
-    first_chunk = false;
-    if (r_next >= p.R) break;
-    __syncthreads();  // the next chunk rewrites the shared tables
+    u += g_end - g_begin;
   }
 }
 
@@ -381,9 +470,9 @@ __global__ void __launch_bounds__(kBwThreads, 2) align_avg_bwd_scatter(const BwP
 int try_launch_avg_bwd_gather(const float* top_diff, float scale, int B, int R, int H, int W, int C,
                               const float* rois, float* bottom_diff, cudaStream_t stream) {
   if (C % kBwCg != 0 || H < 2 || W < 2 || H > kBwMaxDim || W > kBwMaxDim || H * W > kBwCells * kBwThreads) return 0;
-  if ((long long)B * (C / kBwCg) > 0x7fffffffLL) return 0;
-  const size_t smem = (size_t)kBwChunk * 64 * kBwCg * 4 + (size_t)kBwChunk * kBwCg * 49 * 4 +
-                      sizeof(BwAxis) * kBwChunk + sizeof(uchar4) * kBwChunk * (size_t)(H + W);
+  const size_t smem = (size_t)kCsrChunk * 64 * kBwCg * 4 + sizeof(CsrEnt) * kCsrMaxEnt + sizeof(BwAxis) * kCsrChunk;
+  static_assert((size_t)kCsrChunk * 2 * kBwMaxDim * sizeof(uchar4) <= (size_t)kCsrChunk * 64 * kBwCg * 4,
+                "the row / column maps alias the sample-gradient buffer");
   cudaError_t e = cudaFuncSetAttribute(align_avg_bwd_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("roi_align backward: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
@@ -399,11 +488,11 @@ int try_launch_avg_bwd_gather(const float* top_diff, float scale, int B, int R, 
   p.H = H;
   p.W = W;
   p.C = C;
-  // CTAs per frame: each works through kBwGroups channel groups with one set of tables (fewer when C is small)
-  int per_cta = kBwGroups * kBwCg;
-  while (per_cta > kBwCg && C % per_cta != 0) per_cta -= kBwCg;
-  p.splits = C / per_cta;
-  align_avg_bwd_gather<<<B * p.splits, kBwThreads, smem, stream>>>(p);
+  p.splits = 0;
+  const long long units = (long long)B * (C / kBwCg);
+  const long long cap = (long long)sm_count() * 2;  // two CTAs per SM, persistent
+  const int grid = (int)(units < cap ? units : cap);
+  align_avg_bwd_gather<<<grid, kBwThreads, smem, stream>>>(p);
   return launch_status("align_avg_bwd_gather");
 }
 

@@ -19,7 +19,7 @@ COMM_SMS = int(os.environ.get("NAFAE_COMM_SMS", "16"))
 
 
 # largest world size for which make_allreduce("auto") prefers the peer-memory kernel over NVLS
-AUTO_PEER_MAX_WORLD = int(os.environ.get("NAFAE_AUTO_PEER_MAX_WORLD", "2"))
+AUTO_PEER_MAX_WORLD = int(os.environ.get("NAFAE_AUTO_PEER_MAX_WORLD", "4"))
 
 
 def trainable_grad_elems(vis_fc_dim=4096, glove_dim=200, ebd_dim=512):
@@ -288,7 +288,7 @@ class MulticastAllReduce(object):
         self.numel = int(numel)
         self.cta_threads = int(cta_threads if cta_threads is not None else
                                os.environ.get("NAFAE_MC_THREADS", "512"))
-        self.num_ctas = int(num_ctas if num_ctas is not None else os.environ.get("NAFAE_MC_CTAS", "16"))
+        self.num_ctas = int(num_ctas if num_ctas is not None else os.environ.get("NAFAE_MC_CTAS", "8"))
         nbytes = int(_C.lib.nafae_mc_buffer_bytes(self.count, self.world))
         h = ctypes.c_void_p()
         self._h = None
@@ -367,8 +367,9 @@ def make_allreduce(numel, device, kind="auto", peer_kw=None, mc_kw=None):
     if kind not in ("auto", "multicast", "peer"):
         raise ValueError("kind must be auto, multicast or peer")
     if kind == "auto" and dist.get_world_size() <= AUTO_PEER_MAX_WORLD:
-        # measured (profiles/RESULTS.md): with two ranks the in-switch reduction moves MORE bytes over
-        # NVLink than the peer pull / push (every rank's copy travels to the switch), 73 vs 69 us / step
+        # measured (profiles/RESULTS.md, round 2): in the pipelined step the bulk-copy peer kernel is
+        # ahead at 2 and 4 ranks (59.0 vs 61.5 and 60.4 vs 61.5 us / step) and level at 8 (59.9 vs 60.1),
+        # where the NVLS kernel needs half the SMs (8 CTAs) and the RoIAlign kernel keeps 122 instead of 112
         kind = "peer"
     if kind != "peer":
         mine = multicast_supported(device)

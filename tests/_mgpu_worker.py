@@ -147,10 +147,12 @@ for hb in host:
     want.append(gather_all(mine).double().mean(0))
 
 
-def run_dp(kind):
+def run_dp(kind, tensor_cores, gated):
+    """bench.py's schedule: head variant (fp32 FMA / tcgen05), all-reduce behind the residency gate or not,
+    the all-reduce branch on a high-priority stream."""
     steps = [GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], c["C"], c["H"], c["W"], c["n"],
                            pre_nms_topn=c["pre"], Delta=c["Delta"], vis_lam=c["vis_lam"], train=True,
-                           device=dev) for _ in range(2)]
+                           device=dev, tensor_cores=tensor_cores) for _ in range(2)]
     buckets = [parallel.make_allreduce(N, dev, kind=kind) for _ in range(2)]
     for st, b, hb in zip(steps, buckets, host):
         st.grad_word = b.views([(st.NQ, c["D"])])[0]
@@ -158,14 +160,15 @@ def run_dp(kind):
         st.run()
     prev = _C.lib.nafae_set_reserved_sms(32)
     side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-    comm = torch.cuda.Stream(dev)
+    comm = torch.cuda.Stream(dev, priority=-1)
     torch.cuda.synchronize()
     graphs = []
     for j in range(2):
         def ar_branch(cur, j=j):
             comm.wait_stream(cur)
             with torch.cuda.stream(comm):
-                steps[j].wait_gate(1)
+                if gated:
+                    steps[j].wait_gate(1)
                 buckets[j].launch()
             return comm
         graphs.append(capture_pipelined(steps[j], steps[1 - j], side, ar_branch))
@@ -184,17 +187,22 @@ def run_dp(kind):
         same = bool((allr.view(torch.int32) == allr[0].view(torch.int32)).all().item())
         if not (err < 1e-4 and same):
             bad += 1
-            failures.append("pipelined DP step %d (%s): grad_word rel err %.3e, replicas identical %s"
-                            % (k, buckets[0].kind, err, same))
-    log("pipelined DP steps (%s all-reduce, gated): %s" % (buckets[0].kind, "ok" if not bad else "FAILED"))
+            failures.append("pipelined DP step %d (%s, tcgen05 head %s, gated %s): grad_word rel err %.3e, replicas "
+                            "identical %s" % (k, buckets[0].kind, tensor_cores, gated, err, same))
+    log("pipelined DP steps (%s all-reduce, %s, %s head): %s" % (
+        buckets[0].kind, "gated" if gated else "ungated", "tcgen05" if tensor_cores else "fma",
+        "ok" if not bad else "FAILED"))
     _C.lib.nafae_set_reserved_sms(prev)
     for b in buckets:
         b.close()
     del graphs
 
 
-for kind in (("peer", "multicast") if HAVE_MC else ("peer",)):
-    run_dp(kind)
+run_dp("peer", False, True)
+run_dp("peer", True, True)
+if HAVE_MC:
+    run_dp("multicast", False, True)
+    run_dp("multicast", True, False)
 
 # ------------------------------------------------------------- 3. HeadTrainer steps ----
 from nafae_b200.bridge import VisEbd, WordEbd  # noqa: E402

@@ -12,12 +12,12 @@ gpu = pytest.mark.gpu
 RTOL = 1e-4
 
 
-def _step(cfg, seed, dev="cuda:0"):
+def _step(cfg, seed, dev="cuda:0", tensor_cores=False):
     from nafae_b200.pipeline import GroundingStep
     c = synth.CONFIGS[cfg]
     st = GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], c["C"], c["H"], c["W"], c["n"],
                        pre_nms_topn=c["pre"], Delta=c["Delta"], vis_lam=c["vis_lam"], train=c["train"],
-                       device=dev)
+                       device=dev, tensor_cores=tensor_cores)
     b = synth.make_batch(cfg, seed)
     st.load(b)
     return c, b, st
@@ -43,9 +43,13 @@ def _check_against_oracle(c, b, st, check_pooled=True):
     return ref
 
 
+HEADS = pytest.mark.parametrize("tensor_cores", [False, True], ids=["fma_head", "tcgen05_head"])
+
+
 @gpu
-def test_cfg2_step_matches_oracle_and_graph_replay_is_identical():
-    c, b, st = _step("cfg2", 1234)
+@HEADS
+def test_cfg2_step_matches_oracle_and_graph_replay_is_identical(tensor_cores):
+    c, b, st = _step("cfg2", 1234, tensor_cores=tensor_cores)
     st.run()
     torch.cuda.synchronize()
     ref = _check_against_oracle(c, b, st)
@@ -64,9 +68,10 @@ def test_cfg2_step_matches_oracle_and_graph_replay_is_identical():
 
 
 @gpu
-def test_cfg4_dense_stress_zero_padding_and_3200_rois():
+@HEADS
+def test_cfg4_dense_stress_zero_padding_and_3200_rois(tensor_cores):
     """300 proposals/frame -> NMS 0.7 -> top-100 (fewer survive: zero-padded rows) -> RoIAlign."""
-    c, b, st = _step("cfg4", 77)
+    c, b, st = _step("cfg4", 77, tensor_cores=tensor_cores)
     st.run()
     torch.cuda.synchronize()
     rois = st.rois.cpu().numpy()
@@ -83,12 +88,13 @@ def test_cfg2_real_14x14_maps():
 
 
 @gpu
-def test_pipelined_schedule_equals_sequential():
+@HEADS
+def test_pipelined_schedule_equals_sequential(tensor_cores):
     """bench.py's three-branch graphs reorder work across batches, never inside one."""
     from nafae_b200 import _C
     from nafae_b200.pipeline import capture_pipelined
-    c, b0, s0 = _step("cfg2", 1)
-    _, b1, s1 = _step("cfg2", 2)
+    c, b0, s0 = _step("cfg2", 1, tensor_cores=tensor_cores)
+    _, b1, s1 = _step("cfg2", 2, tensor_cores=tensor_cores)
     steps = [s0, s1]
     for st in steps:
         st.run()
