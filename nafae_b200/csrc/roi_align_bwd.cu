@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(kBwThreads, 2) align_avg_bwd_gather(const BwPa
         const int c0 = g * kBwCg;
         __syncthreads();  // index complete / previous group's gather done with gs
         // sample gradients = avg_pool2d(2, 1) backward of the output gradients, layout [RoI][sample][channel]
+#pragma unroll 4
         for (int i = tid; i < n * 64 * kBwCg; i += kBwThreads) {
           const int sidx = i & 63, c = (i >> 6) & (kBwCg - 1), j = i >> 9;
           const int ph = sidx >> 3, pw = sidx & 7;
@@ -351,18 +352,21 @@ __global__ void __launch_bounds__(kBwThreads, 2) align_avg_bwd_gather(const BwPa
 // atomics and stores the finished slab -- which is one contiguous block of (B, C, H, W) -- with bulk
 // async copies (cp.async.bulk shared -> global; cp.reduce...add.f32 when the caller accumulates into an
 // existing tensor).  HBM sees every output byte once and no atomics; the 105 M scatter adds of cfg2
-// stay on chip.  A warp handles one sample ROW of a RoI per pass, lane = (sample column, corner), and
-// walks the 8 channels: footprint address and weight are computed once per lane and reused 8 times
-// (the kernel is instruction-bound: the first version, one sample x 8 channels x 4 corners per warp
-// instruction, executed 225 M warp instructions at cfg2, 260 us).  Lanes of neighbouring sample columns
-// may hit the same cell; the CAS loop behind a shared float atomicAdd resolves that.  The RoIs' output
-// gradients are staged by 16-byte cp.async, double buffered in chunks of kScChunk RoIs.  The order in which warps
+// stay on chip.  A warp handles one sample point per pass, lane = (channel, corner): the 32 addresses
+// of a warp instruction are distinct (and bank-conflict free for even W), so the CAS loop behind a
+// shared float atomicAdd spins only when two WARPS collide.  (Measured alternative: lane = (sample
+// column, corner) walking the 8 channels halves the instruction count but lets neighbouring samples
+// collide inside the warp -- 301 vs 256 us at cfg2, 336 vs 248 us on 14x14 maps.)  The sample gradients
+// (the pool's backward) are formed once per (RoI, channel) in shared memory; the RoIs' output gradients
+// are staged by 16-byte cp.async, double buffered in chunks of kScChunk RoIs.  The order in which warps
 // reach a cell is not fixed: like the reference's atomicAdd the sum is not bitwise reproducible
 // (NAFAE_FLAG_DETERMINISTIC selects the gather kernel above instead).
 constexpr int kScChunk = 8;     // RoIs staged at a time (x2 buffers)
 constexpr int kScIds = 128;     // RoI indices of the frame held at a time
 constexpr int kScBlock = kBwCg * kOut * kOut;   // floats of one RoI's 8-channel gradient block (1568 B)
 constexpr uint32_t kScPiece = 32768;            // bytes per bulk store
+constexpr int kGsStride = 65;                   // floats per (RoI, channel) block of sample gradients: odd, so the
+                                                // 8 channels of one sample sit in 8 different banks
 
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -381,8 +385,8 @@ __global__ void __launch_bounds__(kBwThreads, 2) align_avg_bwd_scatter(const BwP
   const int hw = p.H * p.W;
   float* slab = reinterpret_cast<float*>(sc_smem);                         // [8][H*W]
   float* stage = slab + (size_t)kBwCg * hw;                                // [2][chunk][8][49]
-  float* gs = stage + 2 * kScChunk * kScBlock;                             // [chunk][8][64] sample gradients
-  BwAxis* ax = reinterpret_cast<BwAxis*>(gs + kScChunk * kBwCg * 64);      // [2][chunk]
+  float* gs = stage + 2 * kScChunk * kScBlock;                             // [chunk][8][kGsStride] sample gradients
+  BwAxis* ax = reinterpret_cast<BwAxis*>(gs + kScChunk * kBwCg * kGsStride);      // [2][chunk]
   __shared__ int s_ids[kScIds];
   __shared__ int s_wcnt[kBwWarps];
   __shared__ int s_n, s_next;
@@ -396,8 +400,10 @@ __global__ void __launch_bounds__(kBwThreads, 2) align_avg_bwd_scatter(const BwP
     for (int i = tid; i < kBwCg * hw / 4; i += kBwThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
-  // lane roles inside a sample row: sample column, corner of its bilinear footprint
-  const int pw = lane >> 2, ky = (lane >> 1) & 1, kx = lane & 1;
+  // lane roles: channel, corner of the sample's bilinear footprint -- the 32 addresses of one warp
+  // instruction are distinct (and bank-conflict free for even W)
+  const int c = lane >> 2, ky = (lane >> 1) & 1, kx = lane & 1;
+  float* my_plane = slab + (size_t)c * hw + ky * p.W + kx;
   bool any = false;
 
   int r_next = 0;
@@ -439,22 +445,18 @@ __global__ void __launch_bounds__(kBwThreads, 2) align_avg_bwd_scatter(const BwP
         if (ph > 0 && spw < kOut) v += gg[(ph - 1) * kOut + spw];
         if (ph < kOut && spw > 0) v += gg[ph * kOut + spw - 1];
         if (ph < kOut && spw < kOut) v += gg[ph * kOut + spw];
-        gs[i] = v;
+        gs[(i >> 6) * kGsStride + sidx] = v;
       }
       __syncthreads();
-      // a warp scatters one sample row of one RoI per pass: lane = (sample column, corner), 8 channels in turn
-      for (int it = warp; it < n * 8; it += kBwWarps) {
-        const int j = it >> 3, ph = it & 7;
+      // a warp scatters one sample point per pass: lane = (channel, corner)
+      const float* my_gs = gs + c * kGsStride;
+      for (int it = warp; it < n * 64; it += kBwWarps) {
+        const int j = it >> 6, sidx = it & 63, ph = sidx >> 3, pw = sidx & 7;
         const BwAxis& a = ax[buf * kScChunk + j];
         const int hc = a.hcell[ph], wc = a.wcell[pw];
-        if (hc < 0) continue;  // sample row outside the map (warp-uniform)
+        if (hc < 0 || wc < 0) continue;  // sample outside the map (warp-uniform)
         const float wgt = (ky ? a.h1[ph] : a.h0[ph]) * (kx ? a.w1[pw] : a.w0[pw]);
-        if (wc >= 0) {
-          float* dst = slab + (hc + ky) * p.W + wc + kx;
-          const float* g = gs + (size_t)j * kBwCg * 64 + ph * 8 + pw;
-#pragma unroll
-          for (int c = 0; c < kBwCg; ++c) atomicAdd(dst + (size_t)c * hw, wgt * g[c * 64]);
-        }
+        atomicAdd(my_plane + hc * p.W + wc, wgt * my_gs[j * (kBwCg * kGsStride) + sidx]);
       }
     }
     __syncthreads();  // s_ids and the staging buffers are free again; the slab is complete when this was the last pass
@@ -517,7 +519,7 @@ int try_launch_avg_bwd_scatter(const float* top_diff, float scale, int B, int R,
   if ((long long)B * (C / kBwCg) > 0x7fffffffLL) return 0;
   if ((reinterpret_cast<uintptr_t>(top_diff) & 15) != 0 || (reinterpret_cast<uintptr_t>(bottom_diff) & 15) != 0) return 0;
   const size_t smem = (size_t)kBwCg * H * W * 4 + (size_t)2 * kScChunk * kScBlock * 4 +
-                      (size_t)kScChunk * kBwCg * 64 * 4 + sizeof(BwAxis) * 2 * kScChunk;
+                      (size_t)kScChunk * kBwCg * kGsStride * 4 + sizeof(BwAxis) * 2 * kScChunk;
   if (smem > 200 * 1024) return 0;  // slab does not fit: the generic kernel takes over
   auto* kern = accumulate ? align_avg_bwd_scatter<true> : align_avg_bwd_scatter<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
