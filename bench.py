@@ -134,8 +134,8 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20))  # bounded sample: ~0.5 s of host work per step
-    warm = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 200))  # bounded sample: ~0.14 s of host work per step on 16 cores
+    warm = max(1, min(args.warmup, 5))
     base, ms = time_cpu(args.cfg, steps, warm)
     line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=steps,
                 warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="weak",
@@ -544,7 +544,7 @@ def run_ours(args):
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
-        base, _ = time_cpu(args.cfg, 5, 1)
+        base, _ = time_cpu(args.cfg, 80, 2)  # ~11 s of host work on 16 cores
         line["cpu_baseline"] = base
     print(json.dumps(line))
 
