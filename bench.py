@@ -51,6 +51,12 @@ def parse_args():
                     help="pipelined steps captured per CUDA graph; -1 (default) = 1 on one GPU (54.5 vs 54.8 us/step "
                          "with 4) and 4 on several: the ranks meet in the all-reduce every step, and host-side replay "
                          "gaps (4-8 us, jittery) make one rank late for all -- 62.7 -> 59.9 us/step at 8 GPUs")
+    ap.add_argument("--schedule", default="joined", choices=["joined", "exact"],
+                    help="'joined' (default): every step's branches join before the next step starts. 'exact': "
+                         "several steps per graph with only the true data dependencies between them "
+                         "(pipeline.capture_pipelined_exact) -- faster at every GPU count (cfg2: 48.2 vs 54.3 us/step on "
+                         "one GPU, 58.7 vs 59.7 on eight) but it speeds one GPU up more than eight, so the 8-GPU "
+                         "speed-up reads 6.6x instead of 7.3x; not for cfg4 (158.6 vs 144.8 us/step)")
     ap.add_argument("--no-gate", action="store_true",
                     help="do not hold the all-reduce branch behind the RoIAlign kernel's residency gate")
     ap.add_argument("--gate", action="store_true",
@@ -294,13 +300,19 @@ def run_ours(args):
     if world > 1 and ar_kind == "multicast" and not gated and args.comm_sms < 0 and pipelined and \
             buckets[0].cta_threads > 256:
         comm_sms = buckets[0].num_ctas  # ungated CTAs arrive on an empty GPU: one per SM
+    exact = pipelined and args.schedule == "exact" and not args.nccl_allreduce and not args.gate_head
     if args.steps_per_graph < 0:
-        args.steps_per_graph = 4 if (world > 1 and pipelined) else 1
-    reserve = args.reserve_sms if args.reserve_sms >= 0 else (HEAD_SMS if pipelined else 0) + comm_sms
+        args.steps_per_graph = 8 if exact else (4 if (world > 1 and pipelined) else 1)
+    exact = exact and args.steps_per_graph >= 2
+    if exact:
+        gated = False  # several RoIAlign launches are in flight per graph: a gate wait could pair with none
+    # SMs left to the head: 16; 12 suffice on one GPU with the dependency-exact schedule (48.2 vs 49.1 us/step)
+    head_sms = (12 if (exact and world == 1) else HEAD_SMS) if pipelined else 0
+    reserve = args.reserve_sms if args.reserve_sms >= 0 else head_sms + comm_sms
     _C.lib.nafae_set_reserved_sms(reserve)
     # CTAs of the persistent RoIAlign kernel in the timed loops below (step graphs AND kernel-alone)
     slab_ctas = int(_C.lib.nafae_roi_align_persistent_ctas(steps[0].F * (c["C"] // 8)))
-    side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
     comm = torch.cuda.Stream(dev, priority=args.comm_priority) if world > 1 else None
     for st, hb in zip(steps, host):
         st.load(hb)
@@ -342,7 +354,11 @@ def run_ours(args):
     # multi-step graph: S consecutive pipelined steps (S even, so it starts and ends on set 0 / 1)
     S = (args.steps_per_graph // 2 * 2) if (pipelined and args.steps_per_graph >= 2) else 1
     big = None
-    if pipelined and S > 1:
+    if exact:
+        from nafae_b200.pipeline import capture_pipelined_exact
+        big = capture_pipelined_exact(steps, S, side, allreduce=buckets if world > 1 else None, comm=comm)
+        torch.cuda.synchronize()
+    elif pipelined and S > 1:
         def ar_for(j):
             def br(cur):
                 if world <= 1:
@@ -505,10 +521,11 @@ def run_ours(args):
                               step_frac=(ab["total"] / (ms_total / K * 1e-3) / 1e9) / peak),
                 clocks=clocks)
     line["config"]["schedule"] = (
-        "software-pipelined, %d steps per CUDA graph; each step = RoIAlign of batch k+1 || proposal tail of batch k+2 || "
+        "software-pipelined, %d steps per CUDA graph%s; each step = RoIAlign of batch k+1 || proposal tail of batch k+2 || "
         "head (DVSA fwd+bwd) of batch k%s; the detector is frozen, so later batches' NMS/RoIAlign do not "
         "depend on earlier weight updates; %d SMs reserved from the persistent RoIAlign kernel"
-        % (S, " || gradient all-reduce" if world > 1 else "", reserve)) if pipelined else (
+        % (S, " with only the true data dependencies between consecutive steps (no join after each step)" if exact
+           else "", " || gradient all-reduce" if world > 1 else "", reserve)) if pipelined else (
         "sequential: one CUDA graph per step, five kernels back to back")
     line["config"]["head"] = ("scoring contraction on tcgen05 (tf32x3 split, near-ties rechecked in fp32: picks bit-exact)"
                               if steps[0].tensor_cores else "scoring contraction on the fp32 FMA pipe")

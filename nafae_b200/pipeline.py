@@ -215,3 +215,73 @@ def capture_pipelined_body(align_step, next_step, streams, extra_branch=None, ga
     align_step.run_align()
     for st in joined:
         cur.wait_stream(st)
+
+
+def capture_pipelined_exact(steps, num_steps, streams, allreduce=None, comm=None):
+    """CUDA graph of `num_steps` (even) consecutive software-pipelined steps that carries only the TRUE
+    data dependencies between them, instead of a full join after every step (`capture_pipelined`):
+
+        step s, j = s & 1:   RoIAlign of set j  ||  proposal tail of set 1-j  ||  head of set 1-j
+                             [ ||  all-reduce of bucket j ]
+
+        RoIAlign(set j)   @ s  after  tail(set j) @ s-1                 (reads its rois)
+        tail(set 1-j)     @ s  after  RoIAlign(set 1-j) @ s-1           (rewrites the rois that kernel read)
+        head(set 1-j)     @ s  after  head(set 1-j) @ s-2               (same buffers; stream order)
+                               after  all-reduce(bucket 1-j) @ s-1      (rewrites the bucket)
+        all-reduce(j)     @ s  after  head(set j) @ s-1                 (reduces what it wrote)
+
+    RoIAlign kernels follow each other on the capturing stream, tails on streams[0], the heads of the two
+    sets on streams[1] / streams[2], all-reduces on `comm` (make it a high-priority stream).  The chains
+    slide against each other inside the graph -- the heads run ahead, the RoIAlign kernels run back to
+    back -- so a step costs what the slowest CHAIN needs per step, not the slowest chain plus a join and a
+    replay gap.  Every replay still executes exactly `num_steps` of each kernel.  `allreduce` = the two
+    bucket objects (bucket j = gradients of set j), launched ungated: with several aligned RoIAlign launches
+    in flight a residency-gate wait could pair with none of them."""
+    if num_steps < 2 or num_steps % 2:
+        raise ValueError("num_steps must be even and >= 2")
+    if len(streams) < 3:
+        raise ValueError("capture_pipelined_exact needs three side streams (tails, heads of set 0 / set 1)")
+    if allreduce is not None and comm is None:
+        raise ValueError("an all-reduce branch needs its own stream")
+    tails, heads = streams[0], (streams[1], streams[2])
+    side = [tails, heads[0], heads[1]] + ([comm] if allreduce is not None else [])
+    torch.cuda.current_stream().synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        cur = torch.cuda.current_stream()
+        for st in side:
+            st.wait_stream(cur)
+        ev_align = ev_tail = None          # of the previous step
+        ev_head, ev_ar = [None, None], [None, None]   # latest head / all-reduce touching set / bucket i
+
+        def mark(stream):
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            return ev
+        for s in range(num_steps):
+            j = s & 1
+            if ev_align is not None:
+                tails.wait_event(ev_align)
+            with torch.cuda.stream(tails):
+                steps[1 - j].run_tail()
+                new_tail = mark(tails)
+            if ev_tail is not None:
+                cur.wait_event(ev_tail)
+            steps[j].run_align(gated=False)
+            new_align = mark(cur)
+            if allreduce is not None:
+                if ev_head[j] is not None:
+                    comm.wait_event(ev_head[j])
+                with torch.cuda.stream(comm):
+                    allreduce[j].launch()
+                    ev_ar[j] = mark(comm)
+            h = heads[1 - j]
+            if ev_ar[1 - j] is not None:
+                h.wait_event(ev_ar[1 - j])
+            with torch.cuda.stream(h):
+                steps[1 - j].run_head()
+                ev_head[1 - j] = mark(h)
+            ev_align, ev_tail = new_align, new_tail
+        for st in side:
+            cur.wait_stream(st)
+    return g

@@ -29,6 +29,7 @@ rank, world, local = parallel.init_from_env()
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 TIME = os.environ.get("NAFAE_MGPU_TIME") == "1"
+ONLY_EXACT = os.environ.get("NAFAE_MGPU_ONLY") == "exact"  # dev: just the dependency-exact DP graphs
 N = parallel.trainable_grad_elems()
 failures = []
 
@@ -104,19 +105,20 @@ def check_allreduce(name, ar):
 
 
 # ------------------------------------------------------------------ 1. all-reduce variants ----
-widths = [w for w in (2, 4, 8) if w >= world]
+widths = [w for w in (2, 4, 8) if w >= world] if not ONLY_EXACT else []
 for w in widths:
     for v in (0, 1):
         check_allreduce("peer bulk-copy <W=%d, V=%d> x16" % (w, v),
                         parallel.PeerAllReduce(N, dev, num_ctas=16, cta_threads=0, variant=v, width=w))
-check_allreduce("peer bulk-copy auto width x8", parallel.PeerAllReduce(N, dev, num_ctas=8, cta_threads=0))
-check_allreduce("peer per-thread 256 x96", parallel.PeerAllReduce(N, dev, num_ctas=96, cta_threads=256))
-check_allreduce("peer per-thread 128 x128", parallel.PeerAllReduce(N, dev, num_ctas=128, cta_threads=128))
+if not ONLY_EXACT:
+    check_allreduce("peer bulk-copy auto width x8", parallel.PeerAllReduce(N, dev, num_ctas=8, cta_threads=0))
+    check_allreduce("peer per-thread 256 x96", parallel.PeerAllReduce(N, dev, num_ctas=96, cta_threads=256))
+    check_allreduce("peer per-thread 128 x128", parallel.PeerAllReduce(N, dev, num_ctas=128, cta_threads=128))
 mc_flags = [None] * world
 dist.all_gather_object(mc_flags, parallel.multicast_supported(dev))
 HAVE_MC = all(mc_flags)
 log("NVSwitch multicast supported on every rank: %s" % HAVE_MC)
-if HAVE_MC:
+if HAVE_MC and not ONLY_EXACT:
     for ctas, thr in ((16, 512), (8, 512), (4, 1024), (32, 256), (2, 512)):
         check_allreduce("multicast (NVLS) %dx%d" % (ctas, thr),
                         parallel.MulticastAllReduce(N, dev, num_ctas=ctas, cta_threads=thr))
@@ -125,7 +127,7 @@ if HAVE_MC:
     if ar.kind != want_kind:
         failures.append("make_allreduce(auto) picked %s, expected %s at world %d" % (ar.kind, want_kind, world))
     ar.close()
-else:
+elif not HAVE_MC:
     ar = parallel.make_allreduce(N, dev)
     if ar.kind != "peer":
         failures.append("make_allreduce(auto) must fall back to the peer-memory kernel")
@@ -198,11 +200,58 @@ def run_dp(kind, tensor_cores, gated):
     del graphs
 
 
-run_dp("peer", False, True)
-run_dp("peer", True, True)
+def run_dp_exact(kind, tensor_cores):
+    """bench.py's default schedule: several steps per graph with only the true dependencies between them,
+    the all-reduce ungated on a high-priority stream (pipeline.capture_pipelined_exact)."""
+    from nafae_b200.pipeline import capture_pipelined_exact
+    steps = [GroundingStep(c["Na"], c["Ns"], c["Nb"], c["Ne"], c["D"], c["C"], c["H"], c["W"], c["n"],
+                           pre_nms_topn=c["pre"], Delta=c["Delta"], vis_lam=c["vis_lam"], train=True,
+                           device=dev, tensor_cores=tensor_cores) for _ in range(2)]
+    buckets = [parallel.make_allreduce(N, dev, kind=kind) for _ in range(2)]
+    for st, b, hb in zip(steps, buckets, host):
+        st.grad_word = b.views([(st.NQ, c["D"])])[0]
+        st.load(hb)
+        st.run()
+    prev = _C.lib.nafae_set_reserved_sms(32)
+    side = [torch.cuda.Stream(dev) for _ in range(3)]
+    comm = torch.cuda.Stream(dev, priority=-1)
+    torch.cuda.synchronize()
+    dist.barrier()
+    g = capture_pipelined_exact(steps, 4, side, allreduce=buckets, comm=comm)
+    torch.cuda.synchronize()
+    dist.barrier()
+    bad = 0
+    for k in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    buckets[0].launch()  # flush: the last step's head wrote bucket 0, nobody has reduced it yet
+    torch.cuda.synchronize()
+    for j in range(2):
+        got = steps[j].grad_word.double()
+        err = ((got - want[j]).abs().max() / want[j].abs().max()).item()
+        allr = gather_all(steps[j].grad_word.reshape(-1))
+        same = bool((allr.view(torch.int32) == allr[0].view(torch.int32)).all().item())
+        if not (err < 1e-4 and same):
+            bad += 1
+            failures.append("dependency-exact DP graph (%s, tcgen05 head %s): bucket %d rel err %.3e, replicas "
+                            "identical %s" % (buckets[0].kind, tensor_cores, j, err, same))
+    log("dependency-exact 4-step DP graph (%s all-reduce, %s head): %s" % (
+        buckets[0].kind, "tcgen05" if tensor_cores else "fma", "ok" if not bad else "FAILED"))
+    _C.lib.nafae_set_reserved_sms(prev)
+    for b in buckets:
+        b.close()
+    del g
+
+
+if not ONLY_EXACT:
+    run_dp("peer", False, True)
+    run_dp("peer", True, True)
+run_dp_exact("peer", True)
 if HAVE_MC:
-    run_dp("multicast", False, True)
-    run_dp("multicast", True, False)
+    if not ONLY_EXACT:
+        run_dp("multicast", False, True)
+        run_dp("multicast", True, False)
+    run_dp_exact("multicast", True)
 
 # ------------------------------------------------------------- 3. HeadTrainer steps ----
 from nafae_b200.bridge import VisEbd, WordEbd  # noqa: E402

@@ -76,6 +76,48 @@ def test_random_batches_match_oracle(seed):
 
 
 @gpu
+@pytest.mark.parametrize("Na,Ns,lens", [(1, 800, [9]), (2, 64, [13, 2])])
+def test_eval_shapes_the_reference_runs(Na, Ns, lens):
+    """Evaluation runs whole videos: up to 800 frames of one segment (model.py:851), detector features in
+    64-frame chunks (model.py:436).  Eval phase: picks bit-exact, similarities within 1e-4."""
+    from nafae_b200.grounding import ground
+    Nb, Ne, D = 20, 13, 512
+    rs = np.random.RandomState(Ns)
+    vis = synth.embeddings(rs, Na * Ns * Nb, D)
+    word = synth.embeddings(rs, Na * Ne, D)
+    dev = torch.device("cuda:0")
+    with torch.no_grad():
+        D_ind, D_sim, loss = ground(torch.from_numpy(vis).to(dev), torch.from_numpy(word).to(dev), lens, Na, Nb, Ne,
+                                    10.0, 4.13, False)
+    ref = odvsa.dvsa_forward_backward(vis, word, lens, Na, Nb, Ne, 10.0, 4.13, "eval")
+    live = _live_mask(dict(Na=Na, Ne=Ne, lens=lens))
+    np.testing.assert_array_equal(D_ind.cpu().numpy()[:, live], ref["D_ind"][:, live])
+    np.testing.assert_allclose(D_sim.cpu().numpy(), ref["D_sim"], rtol=RTOL, atol=1e-5)
+
+
+@gpu
+def test_train_phase_limits_are_clear_errors():
+    """Shapes outside the kernels' limits fail with a message, never with wrong results."""
+    from nafae_b200 import _C
+    from nafae_b200.grounding import ground
+    dev = torch.device("cuda:0")
+
+    def call(Na, Ns, Nb, Ne, D, train):
+        v = torch.zeros((Na * Ns * Nb, D), device=dev)
+        w = torch.zeros((Na * Ne, D), device=dev)
+        return ground(v, w, [1] * Na, Na, Nb, Ne, 10.0, 4.13, train)
+    with pytest.raises(_C.NafaeError, match="at most 64 frames"):
+        call(1, 65, 4, 3, 64, True)
+    call(1, 65, 4, 3, 64, False)  # the eval phase has no such limit
+    with pytest.raises(_C.NafaeError, match="max_ent_len"):
+        call(1, 2, 4, 17, 64, True)
+    with pytest.raises(_C.NafaeError, match="exceeds"):
+        call(200, 1, 2, 16, 64, True)  # Na * Ne = 3200 query slots
+    with pytest.raises(_C.NafaeError, match="multiple of 4"):
+        call(1, 2, 4, 3, 66, True)
+
+
+@gpu
 def test_small_delta_activates_and_deactivates_hinges():
     rs = np.random.RandomState(7)
     Na, Ns, Nb, Ne, D = 4, 3, 6, 5, 64

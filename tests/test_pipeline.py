@@ -117,6 +117,38 @@ def test_pipelined_schedule_equals_sequential(tensor_cores):
 
 
 @gpu
+@HEADS
+def test_dependency_exact_multi_step_graph_equals_sequential(tensor_cores):
+    """capture_pipelined_exact: 4 steps per graph with only the true dependencies between them; three
+    replays (12 steps over the two buffer sets) must leave exactly what sequential runs leave."""
+    from nafae_b200 import _C
+    from nafae_b200.pipeline import capture_pipelined_exact
+    c, b0, s0 = _step("cfg2", 1, tensor_cores=tensor_cores)
+    _, b1, s1 = _step("cfg2", 2, tensor_cores=tensor_cores)
+    steps = [s0, s1]
+    for st in steps:
+        st.run()
+    torch.cuda.synchronize()
+    want = [[t.clone() for t in (st.rois, st.pooled, st.D_ind, st.loss, st.grad_word)] for st in steps]
+    prev = _C.lib.nafae_set_reserved_sms(16)
+    try:
+        side = [torch.cuda.Stream() for _ in range(3)]
+        g = capture_pipelined_exact(steps, 4, side)
+        for st in steps:  # scribble over the outputs so that the replays must recompute them
+            st.pooled.zero_(); st.rois.zero_(); st.D_ind.zero_(); st.grad_word.zero_(); st.loss.zero_()
+        for i in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+    finally:
+        _C.lib.nafae_set_reserved_sms(prev)
+    for st, w in zip(steps, want):
+        for a, t in zip(w, (st.rois, st.pooled, st.D_ind, st.loss, st.grad_word)):
+            assert torch.equal(a, t)
+    with pytest.raises(ValueError):
+        capture_pipelined_exact(steps, 3, side)
+
+
+@gpu
 def test_cfg5_inference_sweep_sample_picks_and_boxes():
     """cfg5 = 10k eval segments sharded over ranks; here a 48-segment shard of rank 1 of 8: picks
     (bit-exact) and the recorded boxes equal the oracle's (postprocess + record_det)."""

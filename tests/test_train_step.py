@@ -87,7 +87,13 @@ def test_head_trainer_three_steps_match_a_stock_pytorch_loop():
         live = np.zeros((Na, Ne), bool)
         for a, k in enumerate(lens):
             live[a, :k] = True
-        np.testing.assert_array_equal(D_ind.cpu().numpy()[:, live.reshape(-1)], o_ind.numpy()[:, live.reshape(-1)])
+        # the embeddings come from cuBLAS here and from the CPU GEMM there (~1e-6 apart): a pick may flip only
+        # where the two best boxes tie to that precision, and then the similarities still agree
+        lv = live.reshape(-1)
+        ours, theirs = D_ind.cpu().numpy()[:, lv], o_ind.numpy()[:, lv]
+        flip = ours != theirs
+        assert flip.mean() <= 0.02, flip.mean()
+        np.testing.assert_allclose(D_sim.detach().cpu().numpy()[:, lv], o_sim.detach().numpy()[:, lv], rtol=1e-4, atol=2e-5)
     got = tr.flat_param.cpu()
     want = torch.cat([q.detach().reshape(-1) for q in ref_params])
     # Adam's first steps move every weight by ~lr * sign-like(m / sqrt(v)) whatever the gradient's
