@@ -149,8 +149,7 @@ def run_reference(args):
                 data="synthetic", impl="reference", config=workload_config(args.cfg, 1),
                 cpu_baseline=base,
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    line["config"]["note"] = ("CPU arm runs one replica on rank 0's host cores regardless of "
-                              "--gpus (world=%d)" % world)
+    line["note"] = "CPU arm runs one replica on rank 0's host cores regardless of --gpus (world=%d)" % world
     print(json.dumps(line))
 
 
@@ -520,20 +519,21 @@ def run_ours(args):
                               algorithmic_bytes=ab["total"], peak_source=peak_src,
                               step_frac=(ab["total"] / (ms_total / K * 1e-3) / 1e9) / peak),
                 clocks=clocks)
-    line["config"]["schedule"] = (
+    line["run"] = {}  # how this arm executed the workload (kept out of `config`, which both arms share)
+    line["run"]["schedule"] = (
         "software-pipelined, %d steps per CUDA graph%s; each step = RoIAlign of batch k+1 || proposal tail of batch k+2 || "
         "head (DVSA fwd+bwd) of batch k%s; the detector is frozen, so later batches' NMS/RoIAlign do not "
         "depend on earlier weight updates; %d SMs reserved from the persistent RoIAlign kernel"
         % (S, " with only the true data dependencies between consecutive steps (no join after each step)" if exact
            else "", " || gradient all-reduce" if world > 1 else "", reserve)) if pipelined else (
         "sequential: one CUDA graph per step, five kernels back to back")
-    line["config"]["head"] = ("scoring contraction on tcgen05 (tf32x3 split, near-ties rechecked in fp32: picks bit-exact)"
+    line["run"]["head"] = ("scoring contraction on tcgen05 (tf32x3 split, near-ties rechecked in fp32: picks bit-exact)"
                               if steps[0].tensor_cores else "scoring contraction on the fp32 FMA pipe")
     if world > 1:
         line["replicas_identical"] = replicas_identical
-        line["config"]["allreduce_kind"] = ar_kind
+        line["run"]["allreduce_kind"] = ar_kind
     if world > 1 and ar_kind == "multicast":
-        line["config"]["allreduce"] = (
+        line["run"]["allreduce"] = (
             "NVLS all-reduce (AVG) per step over a flat fp32 bucket of %d elems (%.1f MB): allreduce_mc_kernel, "
             "multimem.ld_reduce in the NVSwitch + multimem.st broadcast, %d CTAs x %d threads, a parallel branch "
             "of the NEXT step's CUDA graph on a high-priority stream%s; %d SMs left free for it"
@@ -550,7 +550,7 @@ def run_ours(args):
         else:
             ar_name = ("two-shot NVLink peer-memory kernel (allreduce_avg_kernel, %d CTAs x %d threads)"
                        % (buckets[0].num_ctas, buckets[0].cta_threads))
-        line["config"]["allreduce"] = (
+        line["run"]["allreduce"] = (
             "%s all-reduce (AVG) per step over a flat fp32 bucket of %d elems (%.1f MB), a parallel branch of the NEXT "
             "step's CUDA graph on a high-priority stream (overlaps its NMS/RoIAlign%s); %d SMs left free for it"
             % (ar_name, parallel.trainable_grad_elems(), parallel.trainable_grad_elems() * 4 / 1e6,

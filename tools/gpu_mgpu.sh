@@ -22,7 +22,7 @@ try:
     d = json.loads(open(out + '/b.json').read().strip().splitlines()[-1])
     print("%-46s N=%d %8.0f seg/s %6.1f us/step  align %5.1f us (%d CTAs) kind=%s identical=%s" % (
         sys.argv[1], d["n_gpus"], d["value"], d["ms_per_step"] * 1e3, d["roofline"]["kernel_us"],
-        d["roofline"]["kernel_grid_sms"], d["config"].get("allreduce_kind"), d.get("replicas_identical")))
+        d["roofline"]["kernel_grid_sms"], d.get("run", {}).get("allreduce_kind"), d.get("replicas_identical")))
 except Exception as e:
     print(sys.argv[1], "failed", e, open(out + '/b.err').read()[-800:])
 PY
