@@ -40,6 +40,19 @@ def test_library_exports_every_declared_symbol():
     assert lib.nafae_abi_version() == 3 == _C.ABI_VERSION
 
 
+def test_python_constants_equal_the_header_macros():
+    """Flags and pooling modes are passed as plain integers through ctypes: they must be the header's."""
+    import re
+    from nafae_b200 import _C
+    hdr = open(os.path.join(ROOT, "include", "nafae_b200.h")).read()
+    macros = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+NAFAE_(\w+)\s+(\d+)u?\b", hdr)}
+    for name in ("FLAG_EXACT", "FLAG_NO_GATE", "FLAG_OUT_BF16", "FLAG_OVERWRITE", "FLAG_DETERMINISTIC",
+                 "POOL_NONE", "POOL_AVG", "POOL_MAX"):
+        assert macros[name] == getattr(_C, name), name
+    flags = [v for k, v in macros.items() if k.startswith("FLAG_")]
+    assert len(set(flags)) == len(flags) and all(v & (v - 1) == 0 for v in flags)  # distinct single bits
+
+
 def test_invalid_arguments_return_zero_without_a_gpu():
     """Argument validation happens before any CUDA call: status 0 + message, never exit()."""
     from nafae_b200 import _C

@@ -85,3 +85,22 @@ def test_pool2x2_matches_aten_cpu():
         fn(tt, 2, 1).backward(torch.from_numpy(gy))
         got = ocpu.pool2x2_backward(np.nan_to_num(x), gy, is_max)
         np.testing.assert_allclose(got, tt.grad.numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_roi_align_avg_backward_is_the_adjoint_of_the_forward():
+    """Size-independent property that ties the checker's two directions together: RoIAlignAvg is linear
+    in the features, so <forward(x), g> == <x, backward(g)> (the GPU backward kernels are compared
+    against this backward, the forward against reference-GPU fixtures)."""
+    from nafae_b200 import synth
+    rs = np.random.RandomState(5)
+    F, C, H, W, k = 3, 8, 20, 26, 7
+    feat = (synth.conv5_maps(rs, F, C, H, W) - 0.3).astype(np.float32)
+    props, _ = synth.proposals(rs, F, k, H * 16, W * 16)
+    rois = np.concatenate([np.repeat(np.arange(F, dtype=np.float32), k)[:, None], props.reshape(-1, 4)], 1)
+    rois[3, 1:] = 0  # a zero-padded proposal row
+    g = rs.randn(F * k, C, 7, 7).astype(np.float32)
+    y = ocpu.roi_align_avg_forward(feat, rois, 7, 7, 1 / 16.)
+    gx = ocpu.roi_align_avg_backward(g, feat, rois, 1 / 16.)
+    lhs = float((y.astype(np.float64) * g).sum())
+    rhs = float((feat.astype(np.float64) * gx).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
